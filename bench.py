@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py - 1080p frames/s of the DCT-QIM embed+extract round trip on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): 1800 synthetic 1920x1080 BGR frames PER GPU, 63 AC
+coefficients per block (maximum capacity), delta 20, payload = random bits filling every frame.
+One step = one pass of the hot path over that batch: embed every frame (BGR in, gray stego
+out), then extract every stego frame (packed bits out); with N > 1 each rank owns a contiguous
+frame range + its payload slice and the extracted bitstreams are all-gathered over NCCL.
+Inputs are resident in HBM for `value`; `e2e` runs the same round trip through the host-buffer
+C ABI (pinned host memory, H2D + D2H inside the timed region).  See DESIGN.md section 6.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, CH = 1080, 1920, 3
+FRAMES_PER_GPU = int(os.environ.get("SVS_BENCH_FRAMES", "1800"))
+NUM_AC, DELTA = 63, 20
+LO, HI = 64, 192            # mid-range noise: the reference's own round trip is error-free here
+METRIC = "1080p frames/s embed+extract (device-timed)"
+UNIT = "frames/s"
+
+
+def workload_name():
+    return "1080p x %d frames per GPU, BGR u8, 63 AC, delta 20, uniform[64,192) noise" % FRAMES_PER_GPU
+
+
+def algorithmic_bytes(frames, cap_bits):
+    """embed = 3HW + HW + cap/8, extract(gray) = HW + cap/8 per frame."""
+    px = H * W
+    nb = (cap_bits + 7) // 8
+    return frames * (3 * px + px + nb), frames * (px + nb)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per embed launch from the last committed `ncu --set full` capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if t.get("frames") and t.get("embed_dram_bytes"):
+            return t["embed_dram_bytes"] / t["frames"] * FRAMES_PER_GPU
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, smax, reasons, power = [], 0.0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = max(smax, float(r[2]))
+                power = max(power, float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "power_w_max": power or None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def _port_round_trip(seed):
+    """One 1080p/63 round trip through the loop-structured port of the reference (one process)."""
+    import numpy as np
+    from oracle import ref_port
+    from tests.synth import synth_frames, synth_bits, bits_to_str
+    frame = synth_frames("cpu%d" % seed, (H, W, CH), LO, HI)
+    cap = (H // 8) * (W // 8) * NUM_AC
+    seg = bits_to_str(synth_bits("cpu%d" % seed, cap))
+    t0 = time.perf_counter()
+    _, stego, k = ref_port.proses_frame_qim_dct(frame, 'embed', DELTA, seg, num_ac_coeffs_to_use=NUM_AC)
+    out = ref_port.proses_frame_qim_dct(stego, 'extract', DELTA, num_ac_coeffs_to_use=NUM_AC)
+    dt = time.perf_counter() - t0
+    assert k == cap and out == seg
+    return dt
+
+
+def cpu_port_baseline(frames_per_proc=1, max_procs=None):
+    """Reference-structured CPU path on all host cores: one process per core, disjoint frames."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    if max_procs:
+        cores = min(cores, max_procs)
+    ctx = mp.get_context("spawn")
+    jobs = list(range(cores * frames_per_proc))
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        per = pool.map(_port_round_trip, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(per) * frames_per_proc
+    return {"value": len(jobs) / busy, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d frames (1 per process x %d processes) of the 1080p/63-AC/delta-20 round trip through "
+                      "oracle/ref_port.py (per-block scipy.fftpack + per-coefficient round(), the reference's own "
+                      "loop structure); rate = frames / slowest process time; pool wall %.1fs" % (len(jobs), cores, wall),
+            "per_core_frames_per_s": 1.0 / statistics.mean(per)}
+
+
+def cpu_c_oracle_rate(frames=32):
+    """The plain-C op-exact oracle, all host threads (a far stronger CPU figure than the reference)."""
+    import numpy as np
+    from oracle import c_oracle
+    from tests.synth import synth_frames, synth_bits
+    threads = c_oracle.max_threads()
+    f = synth_frames("cpuc", (frames, H, W, CH), LO, HI)
+    cap = (H // 8) * (W // 8) * NUM_AC
+    packed = np.packbits(synth_bits("cpuc", frames * cap))
+    t0 = time.perf_counter()
+    stego, _, _ = c_oracle.embed_frames(f, packed, frames * cap, DELTA, NUM_AC, threads=threads, want_gray=False)
+    c_oracle.extract_frames(stego, DELTA, NUM_AC, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d frames through oracle/dctqim_oracle.c (op-exact plain C, pthreads)" % frames}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_port_baseline(frames_per_proc=1)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = statistics.mean(vals)
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * last["cores"] / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "step": "one 1080p round trip per host core (bounded sample)"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import svs_b200
+    from svs_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    F = FRAMES_PER_GPU
+    cap = svs_b200.capacity_bits(H, W, NUM_AC)
+    nbytes = (cap + 7) // 8
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    frames = torch.randint(LO, HI, (F, H, W, CH), dtype=torch.uint8, device=dev, generator=gen)
+    payload = torch.randint(0, 256, (F * nbytes,), dtype=torch.uint8, device=dev, generator=gen)
+    total_bits = F * cap
+    stego = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+    pitch = svs_b200.bits_row_bytes(H, W, NUM_AC)
+    bits = torch.empty((F, pitch), dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world * F, pitch), dtype=torch.uint8, device=dev) if world > 1 else None
+    L = svs_b200.lib()
+    stream = torch.cuda.current_stream()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def step(timed):
+        e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if timed else (None,) * 4
+        if timed:
+            e0.record(stream)
+        svs_b200.embed_frames(frames, payload, total_bits, DELTA, NUM_AC, out=stego)
+        if timed:
+            e1.record(stream)
+        svs_b200.extract_frames(stego, DELTA, NUM_AC, out=bits)
+        if timed:
+            e2.record(stream)
+        if world > 1:
+            sharding.all_gather_bits(bits, out=gathered)
+        if timed:
+            e3.record(stream)
+            marks.append((e0, e1, e2, e3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = L.svs_kernel_launch_count()
+    barrier()
+    t_wall0 = time.time()
+    start, stop = ev(), ev()
+    start.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    stop.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = L.svs_kernel_launch_count() - launches0
+    ms_total = start.elapsed_time(stop)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    embed_ms = statistics.mean(a.elapsed_time(b) for a, b, _, _ in marks)
+    extract_ms = statistics.mean(b.elapsed_time(c) for _, b, c, _ in marks)
+    gather_ms = statistics.mean(c.elapsed_time(d) for _, _, c, d in marks)
+    t = torch.tensor([ms_total, embed_ms, extract_ms, gather_ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, embed_ms, extract_ms, gather_ms = tmax[:4].tolist()
+        launches = int(tsum[4].item())
+
+    # correctness of what was timed: mid-range frames -> the round trip returns the payload
+    ok = bool(torch.equal(bits[:, :nbytes].reshape(-1), payload))
+    if world > 1:
+        mine = gathered[rank * F:(rank + 1) * F, :nbytes].reshape(-1)
+        ok = ok and bool(torch.equal(mine, payload))
+
+    # ---------------- e2e through the host-buffer C ABI (pinned host memory) ----------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world, cap, nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    value = world * F / (ms_per_step / 1000.0)
+    eb, xb = algorithmic_bytes(F, cap)
+    peak, peak_src = measured_peak()
+    ach = eb / (embed_ms / 1000.0) / 1e9
+    ach_x = xb / (extract_ms / 1000.0) / 1e9
+    ach_rt = (eb + xb) / ((embed_ms + extract_ms) / 1000.0) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "frames_per_gpu": F, "height": H, "width": W, "num_ac": NUM_AC,
+                   "delta": DELTA, "step": "embed (BGR->gray stego) + extract (gray stego->packed bits)"
+                                           + (" + NCCL all-gather of bits" if world > 1 else ""),
+                   "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % ((eb + xb) / 1e9),
+                   "parallelism": "frame-sharded x%d" % world},
+        "mpixel_per_s": value * H * W / 1e6,
+        "roofline": {"bound": "hbm", "kernel": "embed_kernel<3,1>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": eb, "launch_ms": embed_ms},
+        "roofline_extract": {"bound": "hbm", "kernel": "extract_kernel<1>", "achieved": ach_x, "peak": peak,
+                             "unit": "GB/s", "frac": ach_x / peak, "algorithmic_bytes_per_launch": xb,
+                             "launch_ms": extract_ms},
+        "roofline_round_trip": {"achieved": ach_rt, "peak": peak, "unit": "GB/s", "frac": ach_rt / peak},
+        "allgather_ms": gather_ms if world > 1 else 0.0,
+        "gpu_launches": launches, "clocks": clocks, "parity_check": ok,
+        "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_port_baseline(frames_per_proc=1)
+            line["cpu_baseline_c_oracle"] = cpu_c_oracle_rate()
+        except Exception as exc:                       # the GPU numbers stay valid without it
+            line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("round trip did not return the payload")
+
+
+def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world, cap, nbytes):
+    """Same round trip through svs_*_frames_host: pinned host buffers, copies inside the timing."""
+    import ctypes
+    L = svs_b200.lib()
+    F = frames.shape[0]
+    steps = max(1, min(args.steps, int(os.environ.get("SVS_BENCH_E2E_STEPS", "3"))))
+    try:
+        h_frames = torch.empty(frames.shape, dtype=torch.uint8).pin_memory()
+        h_frames.copy_(frames)
+        h_payload = payload.cpu().pin_memory()
+        h_stego = torch.empty((F, H, W), dtype=torch.uint8).pin_memory()
+        h_bits = torch.empty((F, nbytes), dtype=torch.uint8).pin_memory()
+    except Exception as exc:
+        return {"error": "pinned allocation failed: %r" % (exc,)}
+    ctx = ctypes.c_void_p()
+    svs_b200._native.check(L.svs_ctx_create(local_rank, 3 << 30, ctypes.byref(ctx)), "svs_ctx_create")
+
+    def one():
+        rc = L.svs_embed_frames_host(ctx, h_frames.data_ptr(), CH, F, H, W, H * W * CH, W * CH,
+                                     h_payload.data_ptr(), 0, F * cap, float(DELTA), NUM_AC,
+                                     h_stego.data_ptr(), 1, None, None, None)
+        svs_b200._native.check(rc, "svs_embed_frames_host")
+        rc = L.svs_extract_frames_host(ctx, h_stego.data_ptr(), 1, F, H, W, H * W, W, float(DELTA), NUM_AC,
+                                       h_bits.data_ptr(), nbytes)
+        svs_b200._native.check(rc, "svs_extract_frames_host")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    one()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    ok = bool(torch.equal(h_bits.reshape(-1), h_payload))
+    L.svs_ctx_destroy(ctx)
+    px = H * W
+    return {"value": world * F * steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": F * (3 * px + nbytes + px), "d2h_bytes_per_step": F * (px + nbytes),
+            "steps": steps, "ms_per_step": 1000.0 * dt / steps, "parity_check": ok,
+            "api": "svs_embed_frames_host + svs_extract_frames_host (C ABI, pinned host buffers, 3-stream chunk pipeline)"}
+
+
+if __name__ == "__main__":
+    main()

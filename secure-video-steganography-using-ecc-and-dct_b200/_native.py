@@ -1,0 +1,110 @@
+"""Loader (and in-tree builder) of libsvs_b200.so - the C ABI declared in include/svs_b200.h.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device can run
+it, every compute entry point raises.  ctypes signatures mirror include/svs_b200.h one to one.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
+HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_ROOT, "include", "svs_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+_lib = None
+
+
+class SvsError(RuntimeError):
+    """A non-zero return code of the C ABI that is not an argument error."""
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libsvs_b200.so")
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile the kernels for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"),
+                                    "-o", LIB_PATH] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_c = ctypes
+_SIGNATURES = {
+    "svs_version": (_c.c_int, []),
+    "svs_last_error_string": (_c.c_char_p, []),
+    "svs_capacity_bits": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
+    "svs_bits_row_bytes": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
+    "svs_kernel_launch_count": (_c.c_int64, []),
+    "svs_extract_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
+                                      _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p]),
+    "svs_embed_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
+                                    _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_double, _c.c_int,
+                                    _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p,
+                                    _c.c_void_p, _c.c_void_p]),
+    "svs_ctx_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
+    "svs_ctx_destroy": (_c.c_int, [_c.c_void_p]),
+    "svs_extract_frames_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                           _c.c_int64, _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64]),
+    "svs_embed_frames_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                         _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_double,
+                                         _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded C ABI.  Raises if the library has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libsvs_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "this package has no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().svs_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    """Argument errors (<0) -> ValueError, CUDA errors (>0) -> SvsError."""
+    if rc == 0:
+        return
+    msg = "%s failed (%d): %s" % (what, rc, last_error())
+    if rc < 0:
+        raise ValueError(msg)
+    raise SvsError(msg)

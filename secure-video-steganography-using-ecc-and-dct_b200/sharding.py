@@ -1,0 +1,110 @@
+"""Frame-sharded multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
+
+The path shards by frame: frame f only needs payload bits
+[f*cap, (f+1)*cap), so rank r owns a contiguous frame range and the matching payload slice and
+embeds with no communication.  Extraction has one real exchange step: every rank ends up with
+the whole bitstream in frame (= payload) order, an all-gather of fixed-size per-frame packed
+bit rows - NCCL over NVLink on GPUs, gloo in the CPU tests of this host logic.
+
+The compute callables default to the CUDA kernels; tests inject CPU stand-ins to exercise the
+partitioning / reassembly logic with world_size 2 on gloo.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import frame_path
+
+
+def frame_range(n_frames, rank, world):
+    """Contiguous, balanced partition: the first n_frames % world ranks get one extra frame."""
+    base, rem = divmod(int(n_frames), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def frame_counts(n_frames, world):
+    return [frame_range(n_frames, r, world)[1] - frame_range(n_frames, r, world)[0] for r in range(world)]
+
+
+def payload_slice(total_bits, cap, f0, f1):
+    """(bit_offset, nbits) of the payload that frames [f0, f1) consume (embed_process.py:115-128)."""
+    total_bits, cap = int(total_bits), int(cap)
+    start = min(total_bits, f0 * cap)
+    stop = min(total_bits, f1 * cap)
+    return start, stop - start
+
+
+def embed_shard(frames_local, payload, total_bits, delta, num_ac, *, n_frames_total, rank=None, world=None,
+                payload_is_global=True, embed_fn=None, **kw):
+    """Embed this rank's frames.  `payload` is either the whole packed payload (every rank holds
+    it; the kernel is pointed at bit f0*cap) or just this rank's slice (payload_is_global=False,
+    which must start at a byte boundary, true whenever cap % 8 == 0)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    embed_fn = embed_fn or frame_path.embed_frames
+    h, w = frames_local.shape[1:3]
+    cap = frame_path.capacity_bits(h, w, num_ac) if delta > 0 else 0
+    f0, f1 = frame_range(n_frames_total, rank, world)
+    if f1 - f0 != frames_local.shape[0]:
+        raise ValueError("rank %d owns frames [%d,%d) but was handed %d" % (rank, f0, f1, frames_local.shape[0]))
+    if payload_is_global:
+        off, nbits = payload_slice(total_bits, cap, f0, n_frames_total)     # everything from f0 on
+        if cap == 0:
+            off, nbits = 0, int(total_bits)
+        return embed_fn(frames_local, payload, nbits, delta, num_ac, bit_offset=off, **kw)
+    return embed_fn(frames_local, payload, int(total_bits), delta, num_ac, bit_offset=0, **kw)
+
+
+def all_gather_bits(local_bits, out=None, counts=None, group=None):
+    """All-gather per-frame packed bit rows -> (sum(counts), row_bytes) in frame order on every rank.
+
+    Equal shard sizes take one all_gather_into_tensor straight into `out`; ragged shards are
+    padded to the largest count and trimmed after the exchange.
+    """
+    world = dist.get_world_size(group)
+    local_bits = local_bits if local_bits.is_contiguous() else local_bits.contiguous()
+    nloc, row = local_bits.shape
+    if counts is None:
+        counts = [nloc] * world
+    if len(set(counts)) == 1:
+        if out is None:
+            out = torch.empty((world * nloc, row), dtype=local_bits.dtype, device=local_bits.device)
+        dist.all_gather_into_tensor(out, local_bits, group=group)
+        return out
+    big = max(counts)
+    send = local_bits
+    if nloc < big:
+        send = torch.zeros((big, row), dtype=local_bits.dtype, device=local_bits.device)
+        send[:nloc] = local_bits
+    recv = torch.empty((world * big, row), dtype=local_bits.dtype, device=local_bits.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    parts = [recv[r * big:r * big + c] for r, c in enumerate(counts)]
+    res = torch.cat(parts, 0)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def extract_allgather(frames_local, delta, num_ac, *, n_frames_total=None, group=None, extract_fn=None,
+                      local_out=None, out=None):
+    """Extract this rank's frames and all-gather: returns (F_total, ceil(cap/8)) packed bits in
+    frame order, identical on every rank."""
+    world = dist.get_world_size(group)
+    extract_fn = extract_fn or frame_path.extract_frames
+    local = extract_fn(frames_local, delta, num_ac) if local_out is None else extract_fn(frames_local, delta, num_ac, out=local_out)
+    nbytes = local.shape[1]
+    counts = None
+    if n_frames_total is not None:
+        counts = frame_counts(n_frames_total, world)
+    # gather the padded rows if the extract buffer has a pitch (avoids a compaction copy)
+    base = local
+    if local_out is not None and local_out.shape[1] != nbytes:
+        base = local_out
+    elif not local.is_contiguous() and getattr(local, "_base", None) is not None \
+            and local._base.dim() == 2 and local._base.shape[0] == local.shape[0]:
+        base = local._base
+    full = all_gather_bits(base, out=out, counts=counts, group=group)
+    return full[:, :nbytes]

@@ -1,0 +1,346 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the oracle and against the reference's golden vectors.  Nothing here reads
+/root/reference.  Bar: bit-exact extracted bits, 0 differing stego pixels (the north_star
+allows <= 1 LSB; the kernels reproduce the reference's float32 arithmetic op for op)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import svs_b200
+from oracle import c_oracle as oc
+from oracle import dctqim_oracle as onp
+from tests import golden_util as G
+from tests.synth import synth_frames, synth_bits, bits_to_str, gradient_frame
+
+pytestmark = pytest.mark.gpu
+
+THREADS = 8
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev(a):
+    return _torch().from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _embed_gpu(frames, bits, total, delta, n, **kw):
+    torch = _torch()
+    packed = np.packbits(bits) if len(bits) else np.zeros(4, np.uint8)
+    res = svs_b200.embed_frames(_dev(frames), _dev(packed), total, delta, n, want_gray=True,
+                                want_bits_embedded=True, want_sse=True, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _assert_same_pixels(want, got, what):
+    diff = np.abs(want.astype(np.int16) - got.astype(np.int16))
+    assert diff.max() == 0, "%s: %d pixels differ, max |diff| %d" % (what, int((diff > 0).sum()), int(diff.max()))
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+@pytest.mark.parametrize("name", G.case_ids())
+def test_dropin_matches_reference_golden(name):
+    c, frame, bits = G.get_case(name)
+    gray, stego, n = svs_b200.proses_frame_qim_dct(frame, 'embed', c["delta"], bits_to_str(bits),
+                                                   num_ac_coeffs_to_use=c["num_ac"])
+    assert isinstance(n, int) and gray.flags.c_contiguous and stego.flags.c_contiguous
+    G.check_embed(c, gray, stego, n)
+    s = svs_b200.proses_frame_qim_dct(frame, 'extract', c["delta"], num_ac_coeffs_to_use=c["num_ac"])
+    assert isinstance(s, str)
+    G.check_extract(c, np.frombuffer(s.encode(), np.uint8) - 48, "ext_input")
+    s = svs_b200.proses_frame_qim_dct(stego, 'extract', c["delta"], enable_debug_prints_extract=False,
+                                      num_ac_coeffs_to_use=c["num_ac"])
+    G.check_extract(c, np.frombuffer(s.encode(), np.uint8) - 48, "ext_stego")
+
+
+def test_dropin_edge_semantics():
+    f = synth_frames("edge", (16, 24, 3))
+    g, s, n = svs_b200.proses_frame_qim_dct(f, 'embed', 20, None, num_ac_coeffs_to_use=10)
+    assert n == 0 and np.array_equal(g, s) and np.array_equal(g, onp.bgr_to_gray(f))
+    g, s, n = svs_b200.proses_frame_qim_dct(f, 'embed', 20, "", num_ac_coeffs_to_use=10)
+    assert n == 0 and np.array_equal(g, s)
+    assert svs_b200.proses_frame_qim_dct(f, 'extract', 20, num_ac_coeffs_to_use=0) == ""
+    assert svs_b200.proses_frame_qim_dct(f, 'extract', -1, num_ac_coeffs_to_use=10) == "0" * 60
+    assert svs_b200.proses_frame_qim_dct(f, 'other', 20) is None
+    with pytest.raises(ValueError):
+        svs_b200.proses_frame_qim_dct(f, 'embed', 20, "01a1", num_ac_coeffs_to_use=10)
+    with pytest.raises(ValueError):
+        svs_b200.proses_frame_qim_dct(f, 'extract', 1e-6, num_ac_coeffs_to_use=10)
+    # the function must not mutate its input and must accept non-contiguous crops (embed_process.py:113)
+    big = synth_frames("crop", (40, 50, 3))
+    view = big[0:32, 0:48]
+    keep = big.copy()
+    bits = synth_bits("crop", 500)
+    g1, s1, n1 = svs_b200.proses_frame_qim_dct(view, 'embed', 20, bits_to_str(bits), num_ac_coeffs_to_use=10)
+    g2, s2, n2 = onp.embed_frame(np.ascontiguousarray(view), 20, bits, 10)
+    assert np.array_equal(big, keep) and n1 == n2
+    _assert_same_pixels(g2, g1, "gray of crop")
+    _assert_same_pixels(s2, s1, "stego of crop")
+    gv = big[:, :, 1][0:32, 0:48]                    # strided 2-D view
+    assert svs_b200.proses_frame_qim_dct(gv, 'extract', 7) == onp.extract_frame(np.ascontiguousarray(gv), 7)
+
+
+# ------------------------------------------------------------------ batched API vs the C oracle
+@pytest.mark.parametrize("shape,delta,n,frac", [
+    ((4, 480, 640, 3), 20, 10, 0.7),
+    ((3, 480, 640, 3), 20, 63, 1.2),
+    ((3, 480, 640), 7, 63, 0.55),
+    ((5, 64, 72, 3), 3, 17, 0.9),
+    ((2, 720, 1280, 3), 20, 63, 0.8),
+    ((2, 1080, 1920, 3), 20, 63, 1.0),
+    ((2, 1080, 1920, 3), 2.5, 40, 0.51),
+    ((1, 2160, 3840, 3), 20, 63, 1.0),
+])
+def test_batched_embed_extract_match_oracle(shape, delta, n, frac):
+    frames = synth_frames("batch%s%s" % (shape, n), shape)
+    nf, h, w = shape[:3]
+    cap = svs_b200.capacity_bits(h, w, n)
+    total = int(nf * cap * frac) + 3
+    bits = synth_bits("batch%s" % (shape,), total)
+    res = _embed_gpu(frames, bits, total, delta, n)
+    stego, gray, nb = oc.embed_frames(frames, np.packbits(bits), total, delta, n, threads=THREADS)
+    _assert_same_pixels(gray, res.gray.cpu().numpy(), "gray")
+    _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego")
+    assert np.array_equal(nb, res.bits_embedded.cpu().numpy())
+    sse = ((stego.astype(np.int64) - gray.astype(np.int64)) ** 2).reshape(nf, -1).sum(1)
+    assert np.array_equal(sse, res.sse.cpu().numpy())
+    ext = svs_b200.extract_frames(res.stego, delta, n)
+    want = oc.extract_frames(stego, delta, n, threads=THREADS)
+    assert np.array_equal(want, ext.cpu().numpy()), "extract(stego) differs"
+    ext = svs_b200.extract_frames(_dev(frames), delta, n)
+    want = oc.extract_frames(frames, delta, n, threads=THREADS)
+    assert np.array_equal(want, ext.cpu().numpy()), "extract(cover) differs"
+
+
+def test_payload_bit_offset_and_tail_frames():
+    frames = synth_frames("off", (6, 64, 96, 3))
+    n, delta = 63, 20
+    cap = svs_b200.capacity_bits(64, 96, n)
+    off = 45                                             # unaligned start inside the buffer
+    total = 3 * cap + 1000                               # ends mid-frame 3; frames 4,5 untouched
+    bits = synth_bits("off", off + total + 9)
+    res = svs_b200.embed_frames(_dev(frames), _dev(np.packbits(bits)), total, delta, n, bit_offset=off,
+                                want_gray=True, want_bits_embedded=True)
+    stego, gray, nb = oc.embed_frames(frames, np.packbits(bits), total, delta, n, bit_offset=off)
+    _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego")
+    assert res.bits_embedded.cpu().tolist() == nb.tolist() == [cap, cap, cap, 1000, 0, 0]
+    _assert_same_pixels(gray[4:], res.stego.cpu().numpy()[4:], "frames past the payload")
+
+
+def test_bgr_stego_store_and_strided_views():
+    """N2: fused GRAY2BGR store (embed_process.py:126); inputs as strided crops of a larger batch."""
+    torch = _torch()
+    big = synth_frames("views", (3, 72, 104, 3))
+    d_big = _dev(big)
+    view = d_big[:, 0:64, 0:96]                           # row stride 312, frame stride 22464 (both % 8 == 0)
+    n, delta = 32, 8
+    cap = svs_b200.capacity_bits(64, 96, n)
+    bits = synth_bits("views", 3 * cap)
+    res = svs_b200.embed_frames(view, _dev(np.packbits(bits)), 3 * cap, delta, n, stego_channels=3)
+    torch.cuda.synchronize()
+    crop = np.ascontiguousarray(big[:, 0:64, 0:96])
+    stego, _, _ = oc.embed_frames(crop, np.packbits(bits), 3 * cap, delta, n)
+    got = res.stego.cpu().numpy()
+    assert got.shape == (3, 64, 96, 3)
+    for ch in range(3):
+        _assert_same_pixels(stego, got[..., ch], "BGR stego channel %d" % ch)
+    # extract from the 3-channel stego = what the receiver reads back from the FFV1 file
+    ext = svs_b200.extract_frames(res.stego, delta, n).cpu().numpy()
+    assert np.array_equal(np.unpackbits(ext, axis=1)[:, :cap].reshape(-1), bits)
+    # odd offsets -> the byte-load path
+    shifted = d_big[:, 1:65, 3:99]                        # +3 px: 9-byte offset, not 8-aligned
+    ext = svs_b200.extract_frames(shifted, delta, n).cpu().numpy()
+    want = oc.extract_frames(np.ascontiguousarray(big[:, 1:65, 3:99]), delta, n)
+    assert np.array_equal(want, ext)
+    res2 = svs_b200.embed_frames(shifted, _dev(np.packbits(bits)), 3 * cap, delta, n)
+    stego2, _, _ = oc.embed_frames(np.ascontiguousarray(big[:, 1:65, 3:99]), np.packbits(bits), 3 * cap, delta, n)
+    _assert_same_pixels(stego2, res2.stego.cpu().numpy(), "stego of unaligned view")
+    gshift = d_big[:, 1:65, 3:99, 1]                      # gray, element stride 3 -> made contiguous
+    ext = svs_b200.extract_frames(gshift, delta, n).cpu().numpy()
+    want = oc.extract_frames(np.ascontiguousarray(big[:, 1:65, 3:99, 1]), delta, n)
+    assert np.array_equal(want, ext)
+
+
+def test_extract_byte_store_path_matches_word_store_path():
+    """bits_frame_stride == ceil(cap/8) (not a multiple of 4) exercises the byte-store kernel."""
+    torch = _torch()
+    frames = synth_frames("bytes", (3, 40, 56, 3))
+    n, delta = 63, 20
+    cap = svs_b200.capacity_bits(40, 56, n)                # 2205 bits -> 276 bytes (276 % 4 == 0) ...
+    n2 = 9
+    cap2 = svs_b200.capacity_bits(40, 56, n2)              # 315 bits -> 40 bytes; use stride 41
+    for nn, cc, stride in ((n, cap, (cap + 7) // 8 + 1), (n2, cap2, 41)):
+        out = torch.zeros((3, stride), dtype=torch.uint8, device="cuda")
+        got = svs_b200.extract_frames(_dev(frames), delta, nn, out=out).cpu().numpy()
+        want = oc.extract_frames(frames, delta, nn)
+        assert np.array_equal(want, got)
+
+
+# ------------------------------------------------------------------ config 5: delta x AC sweep at 1080p
+@pytest.mark.parametrize("delta", [1, 2, 3, 4, 6, 8, 10, 16, 20, 32, 50, 100])
+def test_delta_ac_sweep_1080p(delta):
+    frame = synth_frames("sweep", (1, 1080, 1920, 3), 64, 192)
+    d_frame = _dev(frame)
+    for n in (1, 10, 32, 63):
+        cap = svs_b200.capacity_bits(1080, 1920, n)
+        bits = synth_bits("sweep%d" % n, cap)
+        packed = np.packbits(bits)
+        res = svs_b200.embed_frames(d_frame, _dev(packed), cap, delta, n)
+        stego, _, _ = oc.embed_frames(frame, packed, cap, delta, n, threads=THREADS, want_gray=False)
+        _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego d=%s n=%d" % (delta, n))
+        got = svs_b200.extract_frames(res.stego, delta, n).cpu().numpy()
+        want = oc.extract_frames(stego, delta, n, threads=THREADS)
+        assert np.array_equal(want, got), "bits d=%s n=%d" % (delta, n)   # same wrong bits as the reference too
+
+
+def test_hostile_frames_match_oracle():
+    """Saturated, flat and structured frames: clipping, exact ties, zero coefficients."""
+    h, w = 64, 128
+    frames = np.stack([
+        np.zeros((h, w, 3), np.uint8), np.full((h, w, 3), 255, np.uint8),
+        np.indices((h, w)).sum(0)[..., None].repeat(3, 2).astype(np.uint8) % 2 * 255,
+        gradient_frame(h, w, 3, seed=3), synth_frames("hostile", (h, w, 3), 250, 256),
+        (np.arange(h * w * 3, dtype=np.uint32).reshape(h, w, 3) % 256).astype(np.uint8),
+    ])
+    for delta in (1, 7, 20, 64):
+        for n in (10, 63):
+            cap = svs_b200.capacity_bits(h, w, n)
+            bits = synth_bits("hostile", len(frames) * cap)
+            res = _embed_gpu(frames, bits, bits.size, delta, n)
+            stego, gray, _ = oc.embed_frames(frames, np.packbits(bits), bits.size, delta, n)
+            _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego d=%d n=%d" % (delta, n))
+            got = svs_b200.extract_frames(res.stego, delta, n).cpu().numpy()
+            assert np.array_equal(oc.extract_frames(stego, delta, n), got)
+
+
+# ------------------------------------------------------------------ properties at BASELINE sizes
+def test_round_trip_recovers_payload_1080p_batch():
+    """Mid-range frames: the reference round trip is error-free, so the
+    extracted stream must equal the payload for the whole batch."""
+    torch = _torch()
+    nf, n, delta = 24, 63, 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    frames = torch.randint(64, 192, (nf, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    cap = svs_b200.capacity_bits(1080, 1920, n)
+    payload = torch.randint(0, 256, (nf * cap // 8,), dtype=torch.uint8, device="cuda", generator=g)
+    res = svs_b200.embed_frames(frames, payload, nf * cap, delta, n, want_bits_embedded=True, want_sse=True)
+    ext = svs_b200.extract_frames(res.stego, delta, n)
+    assert torch.equal(ext.reshape(-1), payload)
+    assert res.bits_embedded.tolist() == [cap] * nf
+    ext2 = svs_b200.extract_frames(res.stego, delta, n)                      # idempotent
+    assert torch.equal(ext, ext2)
+    psnr = [svs_b200.psnr_from_sse(int(s), 1080, 1920) for s in res.sse.tolist()]
+    assert all(23.5 < p < 25.5 for p in psnr), psnr                          # 24.5 dB
+    # spot-check three frames of the batch against the oracle
+    for f in (0, nf // 2, nf - 1):
+        fr = frames[f].cpu().numpy()
+        seg = payload[f * cap // 8:(f + 1) * cap // 8].cpu().numpy()
+        stego, _, _ = oc.embed_frames(fr[None], seg, cap, delta, n, threads=THREADS, want_gray=False)
+        _assert_same_pixels(stego[0], res.stego[f].cpu().numpy(), "frame %d" % f)
+
+
+def test_end_to_end_payload_decrypts():
+    """Config 2: the ECDH/HKDF/AES-GCM/SHA3 payload built by the reference for image64.png goes
+    through embed -> extract on the GPU and must decrypt, verify and reproduce the image."""
+    pytest.importorskip("cryptography")
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import ec
+    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    from cryptography.hazmat.primitives.kdf.hkdf import HKDF
+
+    e = G.load_e2e()
+    frames = synth_frames("e2e", (2, 480, 640, 3), 64, 192)
+    n, delta = 10, 20
+    bitstr = bits_to_str(np.unpackbits(e["payload_packed"])[:e["total_bits"]])
+    collected, idx = "", 0
+    for f in range(2):                                                     # embed_process.py:108-140
+        if idx < len(bitstr):
+            _, stego, k = svs_b200.proses_frame_qim_dct(frames[f], 'embed', delta, bitstr[idx:], num_ac_coeffs_to_use=n)
+            idx += k
+        else:
+            stego = onp.bgr_to_gray(frames[f])
+        collected += svs_b200.proses_frame_qim_dct(np.repeat(stego[..., None], 3, 2), 'extract', delta, num_ac_coeffs_to_use=n)
+    assert idx == e["total_bits"] == 33744
+    bits = np.frombuffer(collected.encode(), np.uint8) - 48
+    assert np.array_equal(bits[:e["total_bits"]], np.unpackbits(e["payload_packed"])[:e["total_bits"]])
+
+    pos = [0]
+
+    def take(nbits):
+        v = bits[pos[0]:pos[0] + nbits]
+        pos[0] += nbits
+        return v
+
+    def take_int(nbits):
+        return int("".join(map(str, take(nbits))), 2)
+
+    def take_bytes():
+        return np.packbits(take(8 * take_int(8))).tobytes()
+
+    width, height = take_int(16), take_int(16)
+    eph_pub, salt, digest, nonce, tag = (take_bytes() for _ in range(5))
+    ct = np.packbits(take(8 * take_int(32))).tobytes()
+    priv = serialization.load_pem_private_key(e["pem"], password=None)
+    shared = priv.exchange(ec.ECDH(), ec.EllipticCurvePublicKey.from_encoded_point(ec.SECP256R1(), eph_pub))
+    key = HKDF(algorithm=hashes.SHA256(), length=32, salt=salt, info=b'kunci aes untuk steganografi video').derive(shared)
+    plain = AESGCM(key).decrypt(nonce, ct + tag, None)                     # raises on a bad tag
+    h3 = hashes.Hash(hashes.SHA3_256())
+    h3.update(plain)
+    assert h3.finalize() == digest == e["sha3"]
+    assert (width, height) == (e["width"], e["height"])
+    assert np.array_equal(np.frombuffer(plain, np.uint8).reshape(height, width), e["image"])
+
+
+# ------------------------------------------------------------------ host-buffer C ABI
+def test_host_api_chunked_pipeline_matches_device_api():
+    torch = _torch()
+    L = svs_b200.lib()
+    ctx = ctypes.c_void_p()
+    # 3 MB of staging -> ~1 MB per slot -> 480x640 BGR frames go through one per chunk
+    assert L.svs_ctx_create(0, 3 << 20, ctypes.byref(ctx)) == 0
+    try:
+        nf, h, w, n, delta = 7, 480, 640, 63, 20
+        frames = synth_frames("hostapi", (nf, h, w, 3))
+        cap = svs_b200.capacity_bits(h, w, n)
+        total = 5 * cap + 77
+        off = 19
+        bits = synth_bits("hostapi", off + total)
+        packed = np.packbits(bits)
+        stego = np.empty((nf, h, w), np.uint8)
+        gray = np.empty((nf, h, w), np.uint8)
+        nb = np.zeros(nf, np.int64)
+        sse = np.zeros(nf, np.uint64)
+        rc = L.svs_embed_frames_host(ctx, frames.ctypes.data, 3, nf, h, w, h * w * 3, w * 3, packed.ctypes.data,
+                                     off, total, float(delta), n, stego.ctypes.data, 1, gray.ctypes.data,
+                                     nb.ctypes.data, sse.ctypes.data)
+        assert rc == 0, svs_b200._native.last_error()
+        s0, g0, n0 = oc.embed_frames(frames, packed, total, delta, n, bit_offset=off, threads=THREADS)
+        _assert_same_pixels(s0, stego, "host-API stego")
+        _assert_same_pixels(g0, gray, "host-API gray")
+        assert nb.tolist() == n0.tolist()
+        assert sse.tolist() == ((s0.astype(np.int64) - g0) ** 2).reshape(nf, -1).sum(1).tolist()
+        nbytes = (cap + 7) // 8
+        out = np.zeros((nf, nbytes + 5), np.uint8)
+        rc = L.svs_extract_frames_host(ctx, stego.ctypes.data, 1, nf, h, w, h * w, w, float(delta), n,
+                                       out.ctypes.data, nbytes + 5)
+        assert rc == 0, svs_b200._native.last_error()
+        assert np.array_equal(out[:, :nbytes], oc.extract_frames(s0, delta, n, threads=THREADS))
+        # pinned host memory path
+        pin = torch.from_numpy(frames).pin_memory()
+        out2 = torch.zeros((nf, nbytes), dtype=torch.uint8).pin_memory()
+        rc = L.svs_extract_frames_host(ctx, pin.data_ptr(), 3, nf, h, w, h * w * 3, w * 3, float(delta), n,
+                                       out2.data_ptr(), nbytes)
+        assert rc == 0
+        assert np.array_equal(out2.numpy(), oc.extract_frames(frames, delta, n, threads=THREADS))
+    finally:
+        assert L.svs_ctx_destroy(ctx) == 0
+
+
+def test_kernels_really_launch():
+    before = svs_b200.lib().svs_kernel_launch_count()
+    svs_b200.proses_frame_qim_dct(synth_frames("count", (16, 16, 3)), 'extract', 20)
+    assert svs_b200.lib().svs_kernel_launch_count() == before + 1
