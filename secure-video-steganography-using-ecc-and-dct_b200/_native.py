@@ -14,7 +14,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_ROOT, "include", "svs_b200.h")]
+HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
+           os.path.join(_ROOT, "include", "svs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
@@ -62,6 +63,7 @@ _SIGNATURES = {
     "svs_capacity_bits": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
     "svs_bits_row_bytes": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
     "svs_kernel_launch_count": (_c.c_int64, []),
+    "svs_debug_force_scalar": (_c.c_int, [_c.c_int]),
     "svs_extract_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
                                       _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p]),
     "svs_embed_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,

@@ -19,9 +19,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "svs_b200.h"
 #include "svs_math.cuh"
+#include "svs_fast.cuh"
 
 namespace {
 
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 4) embed_kernel(const EmbedArgs a)
         if (process) {
             float x[64];
             unpack_gray(g, x);
-            svs::dct2_fwd(x);
+            svs::dct2_fwd(svs::ScalarOps(), x);
             if (k > 0) {
                 uint32_t hi, lo;
                 payload_window(a.payload, a.payload_last_word, a.payload_bit_offset + used, hi, lo);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 4) embed_kernel(const EmbedArgs a)
                     }
                 }
             }
-            svs::dct2_inv(x);
+            svs::dct2_inv(svs::ScalarOps(), x);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 uint32_t lo4 = 0, hi4 = 0;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 4) extract_kernel(const ExtractArgs 
         load_block_gray<CH, ALIGNED>(src, G.row_stride, g);
         float x[64];
         unpack_gray(g, x);
-        svs::dct2_fwd(x);
+        svs::dct2_fwd(svs::ScalarOps(), x);
         uint32_t hi = 0, lo = 0;                 // bit i of this block at (hi:lo) bit 63-i
         const float d32 = G.delta32;
 #pragma unroll
@@ -400,6 +402,77 @@ void launch_extract(const ExtractArgs& a, bool words, unsigned grid, cudaStream_
     else extract_kernel<CH, ALIGNED, false><<<grid, kThreads, 0, st>>>(a);
 }
 
+
+// Constants of the division-free quantiser (svs_fast.cuh).  |c| <= 2040 for any 8x8 block of
+// bytes (orthonormal basis, L1 norm <= 8), so x = c/(2 delta) + 1/4 (embed) and c/delta + 1/2
+// (extract) are bounded and M = 1.5 * 2^(23-k) leaves k fraction bits in the mantissa of M + x.
+// Error budget (units of 2^-k): rounding of the FMA 1/2, reciprocal instead of division 1/4,
+// the reference's own quotient rounding 1/4 -> strictly below 1; the kernels flag 2.
+fast::FastQuant make_fast_quant(double delta)
+{
+    fast::FastQuant q;
+    memset(&q, 0, sizeof q);
+    q.negzero = -0.0f;
+    const float d32 = (float)delta;
+    if (!(delta >= 0x1p-4) || !(delta <= 0x1p20)) return q;
+    {
+        const double xmax = 1020.0 / d32 + 1.5;
+        int k = 22 - (int)std::ceil(std::log2(xmax + 1.0));
+        if (k > 20) k = 20;
+        const double M = 1.5 * std::ldexp(1.0, 23 - k);
+        q.r2 = (float)(0.5 / (double)d32);
+        q.ke = (float)(M + 0.25 + 2.0 * std::ldexp(1.0, -k));
+        q.d2 = 2.0f * d32;
+        const double k0 = -(double)q.d2 * M;
+        q.k0 = (float)k0;
+        q.emask = (1u << k) - 1u;
+        q.ebit = 1u << (k - 1);
+        q.erot = k - 1;
+        q.embed_ok = k >= 8 && (double)q.k0 == k0 && (double)d32 == delta &&
+                     (double)q.ke == M + 0.25 + 2.0 * std::ldexp(1.0, -k);
+    }
+    {
+        const double xmax = 2040.0 / d32 + 1.5;
+        int k = 22 - (int)std::ceil(std::log2(xmax + 1.0));
+        if (k > 20) k = 20;
+        const double M = 1.5 * std::ldexp(1.0, 23 - k);
+        q.r = (float)(1.0 / (double)d32);
+        q.kx = (float)(M + 0.5 + 2.0 * std::ldexp(1.0, -k));
+        q.xmask = (1u << k) - 1u;
+        q.xk = k;
+        q.extract_ok = k >= 8 && (double)q.kx == M + 0.5 + 2.0 * std::ldexp(1.0, -k);
+    }
+    return q;
+}
+
+fast::FastGeom make_fast_geometry(const Geometry& g)
+{
+    fast::FastGeom f;
+    f.frames = g.frames;
+    f.frame_stride = g.frame_stride;
+    f.row_stride = g.row_stride;
+    f.H = g.H;
+    f.W = g.W;
+    f.bw = g.bw;
+    f.bpf = g.bpf;
+    f.tiles_per_frame = (g.bpf + fast::kFastBlocksPerCta - 1) / fast::kFastBlocksPerCta;
+    f.n = g.n;
+    f.delta32 = g.delta32;
+    return f;
+}
+
+bool g_force_scalar = false;     // SVS_FORCE_SCALAR=1: route everything through the scalar kernels
+
+bool fast_enabled()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SVS_FORCE_SCALAR");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1 && !g_force_scalar;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -412,6 +485,13 @@ int svs_version(void) { return 100; }
 const char* svs_last_error_string(void) { return g_err; }
 
 int64_t svs_kernel_launch_count(void) { return g_launches.load(); }
+
+int svs_debug_force_scalar(int on)
+{
+    const int prev = g_force_scalar ? 1 : 0;
+    if (on >= 0) g_force_scalar = on != 0;
+    return prev;
+}
 
 int64_t svs_capacity_bits(int height, int width, int num_ac)
 {
@@ -449,8 +529,18 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool words = aligned_to(d_bits_out, bits_frame_stride, 0, 4) && bits_frame_stride >= (cap + 31) / 32 * 4;
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (channels == 3) { if (al) launch_extract<3, true>(a, words, (unsigned)grid, st); else launch_extract<3, false>(a, words, (unsigned)grid, st); }
-    else               { if (al) launch_extract<1, true>(a, words, (unsigned)grid, st); else launch_extract<1, false>(a, words, (unsigned)grid, st); }
+    const fast::FastQuant fq = make_fast_quant(delta);
+    if (fast_enabled() && al && words && delta > 0 && fq.extract_ok) {
+        fast::FastExtractArgs fa;
+        fa.g = make_fast_geometry(a.g);
+        fa.q = fq;
+        fa.bits = d_bits_out;
+        fa.bits_frame_stride = bits_frame_stride;
+        const long long fgrid = n_frames * fa.g.tiles_per_frame;
+        if (channels == 3) fast::extract_fast_kernel<3><<<(unsigned)fgrid, fast::kFastThreads, 0, st>>>(fa);
+        else fast::extract_fast_kernel<1><<<(unsigned)fgrid, fast::kFastThreads, 0, st>>>(fa);
+    } else if (channels == 3) { if (al) launch_extract<3, true>(a, words, (unsigned)grid, st); else launch_extract<3, false>(a, words, (unsigned)grid, st); }
+    else                      { if (al) launch_extract<1, true>(a, words, (unsigned)grid, st); else launch_extract<1, false>(a, words, (unsigned)grid, st); }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "svs_extract_frames launch");
@@ -504,7 +594,46 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool f64 = (double)(float)delta != delta;
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned gr = (unsigned)grid;
+    // Frames the payload fills completely go to the packed-FP32 kernel; the frame in which the
+    // payload ends and everything after it (and every special case) to the scalar kernel.
+    const fast::FastQuant fq = make_fast_quant(delta);
+    if (fast_enabled() && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr) {
+        long long full = payload_total_bits / a.cap;
+        if (full > n_frames) full = n_frames;
+        if (full > 0) {
+            fast::FastEmbedArgs fa;
+            fa.g = make_fast_geometry(a.g);
+            fa.q = fq;
+            fa.payload = a.payload;
+            fa.payload_bit_offset = payload_bit_offset;
+            fa.payload_last_word = a.payload_last_word;
+            fa.cap = a.cap;
+            fa.stego = d_stego_out;
+            fa.stego_frame_stride = stego_frame_stride;
+            fa.stego_row_stride = stego_row_stride;
+            fa.bits_embedded = d_bits_embedded_out;
+            const unsigned fgrid = (unsigned)(full * fa.g.tiles_per_frame);
+            if (channels == 3) {
+                if (stego_channels == 1) fast::embed_fast_kernel<3, 1><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                else fast::embed_fast_kernel<3, 3><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            } else {
+                if (stego_channels == 1) fast::embed_fast_kernel<1, 1><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                else fast::embed_fast_kernel<1, 3><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            }
+            g_launches.fetch_add(1);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (packed)");
+            if (full == n_frames) return SVS_OK;
+            // the remaining frames: shift every per-frame quantity by `full`
+            a.g.frames += full * frame_stride;
+            a.payload_bit_offset += full * a.cap;
+            a.payload_total_bits -= full * a.cap;
+            a.stego += full * stego_frame_stride;
+            if (a.bits_embedded) a.bits_embedded += full;
+            n_frames -= full;
+        }
+    }
+    const unsigned gr = (unsigned)(n_frames * a.g.tiles_per_frame);
     if (channels == 3) {
         if (stego_channels == 1) { if (al) launch_embed<3, 1, true>(a, f64, gr, st); else launch_embed<3, 1, false>(a, f64, gr, st); }
         else                     { if (al) launch_embed<3, 3, true>(a, f64, gr, st); else launch_embed<3, 3, false>(a, f64, gr, st); }

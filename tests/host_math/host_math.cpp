@@ -4,8 +4,8 @@
 #include "svs_math.cuh"
 
 extern "C" {
-void hm_dct2_fwd(float* blocks, long n) { for (long i = 0; i < n; ++i) svs::dct2_fwd(blocks + 64 * i); }
-void hm_dct2_inv(float* blocks, long n) { for (long i = 0; i < n; ++i) svs::dct2_inv(blocks + 64 * i); }
-void hm_dct8_fwd(float* rows, long n) { for (long i = 0; i < n; ++i) svs::dct8_fwd<1>(rows + 8 * i); }
-void hm_dct8_inv(float* rows, long n) { for (long i = 0; i < n; ++i) svs::dct8_inv<1>(rows + 8 * i); }
+void hm_dct2_fwd(float* blocks, long n) { for (long i = 0; i < n; ++i) svs::dct2_fwd(svs::ScalarOps(), blocks + 64 * i); }
+void hm_dct2_inv(float* blocks, long n) { for (long i = 0; i < n; ++i) svs::dct2_inv(svs::ScalarOps(), blocks + 64 * i); }
+void hm_dct8_fwd(float* rows, long n) { for (long i = 0; i < n; ++i) svs::dct8_fwd<1>(svs::ScalarOps(), rows + 8 * i); }
+void hm_dct8_inv(float* rows, long n) { for (long i = 0; i < n; ++i) svs::dct8_inv<1>(svs::ScalarOps(), rows + 8 * i); }
 }

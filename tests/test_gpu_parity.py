@@ -85,6 +85,14 @@ def test_dropin_edge_semantics():
 
 
 # ------------------------------------------------------------------ batched API vs the C oracle
+@pytest.fixture(params=["packed", "scalar"])
+def kernel_family(request):
+    """Run a test once through the packed-FP32 kernels and once through the scalar kernels."""
+    prev = svs_b200.lib().svs_debug_force_scalar(1 if request.param == "scalar" else 0)
+    yield request.param
+    svs_b200.lib().svs_debug_force_scalar(prev)
+
+
 @pytest.mark.parametrize("shape,delta,n,frac", [
     ((4, 480, 640, 3), 20, 10, 0.7),
     ((3, 480, 640, 3), 20, 63, 1.2),
@@ -95,7 +103,7 @@ def test_dropin_edge_semantics():
     ((2, 1080, 1920, 3), 2.5, 40, 0.51),
     ((1, 2160, 3840, 3), 20, 63, 1.0),
 ])
-def test_batched_embed_extract_match_oracle(shape, delta, n, frac):
+def test_batched_embed_extract_match_oracle(shape, delta, n, frac, kernel_family):
     frames = synth_frames("batch%s%s" % (shape, n), shape)
     nf, h, w = shape[:3]
     cap = svs_b200.capacity_bits(h, w, n)
@@ -108,6 +116,10 @@ def test_batched_embed_extract_match_oracle(shape, delta, n, frac):
     assert np.array_equal(nb, res.bits_embedded.cpu().numpy())
     sse = ((stego.astype(np.int64) - gray.astype(np.int64)) ** 2).reshape(nf, -1).sum(1)
     assert np.array_equal(sse, res.sse.cpu().numpy())
+    # without the optional gray / SSE outputs the full frames take the packed-FP32 kernel
+    lean = svs_b200.embed_frames(_dev(frames), _dev(np.packbits(bits)), total, delta, n, want_bits_embedded=True)
+    _assert_same_pixels(stego, lean.stego.cpu().numpy(), "stego (lean call)")
+    assert np.array_equal(nb, lean.bits_embedded.cpu().numpy())
     ext = svs_b200.extract_frames(res.stego, delta, n)
     want = oc.extract_frames(stego, delta, n, threads=THREADS)
     assert np.array_equal(want, ext.cpu().numpy()), "extract(stego) differs"
@@ -131,7 +143,7 @@ def test_payload_bit_offset_and_tail_frames():
     _assert_same_pixels(gray[4:], res.stego.cpu().numpy()[4:], "frames past the payload")
 
 
-def test_bgr_stego_store_and_strided_views():
+def test_bgr_stego_store_and_strided_views(kernel_family):
     """N2: fused GRAY2BGR store (embed_process.py:126); inputs as strided crops of a larger batch."""
     torch = _torch()
     big = synth_frames("views", (3, 72, 104, 3))
@@ -182,7 +194,7 @@ def test_extract_byte_store_path_matches_word_store_path():
 
 # ------------------------------------------------------------------ config 5: delta x AC sweep at 1080p
 @pytest.mark.parametrize("delta", [1, 2, 3, 4, 6, 8, 10, 16, 20, 32, 50, 100])
-def test_delta_ac_sweep_1080p(delta):
+def test_delta_ac_sweep_1080p(delta, kernel_family):
     frame = synth_frames("sweep", (1, 1080, 1920, 3), 64, 192)
     d_frame = _dev(frame)
     for n in (1, 10, 32, 63):
@@ -197,7 +209,7 @@ def test_delta_ac_sweep_1080p(delta):
         assert np.array_equal(want, got), "bits d=%s n=%d" % (delta, n)   # same wrong bits as the reference too
 
 
-def test_hostile_frames_match_oracle():
+def test_hostile_frames_match_oracle(kernel_family):
     """Saturated, flat and structured frames: clipping, exact ties, zero coefficients."""
     h, w = 64, 128
     frames = np.stack([
@@ -210,7 +222,7 @@ def test_hostile_frames_match_oracle():
         for n in (10, 63):
             cap = svs_b200.capacity_bits(h, w, n)
             bits = synth_bits("hostile", len(frames) * cap)
-            res = _embed_gpu(frames, bits, bits.size, delta, n)
+            res = svs_b200.embed_frames(_dev(frames), _dev(np.packbits(bits)), bits.size, delta, n)
             stego, gray, _ = oc.embed_frames(frames, np.packbits(bits), bits.size, delta, n)
             _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego d=%d n=%d" % (delta, n))
             got = svs_b200.extract_frames(res.stego, delta, n).cpu().numpy()
