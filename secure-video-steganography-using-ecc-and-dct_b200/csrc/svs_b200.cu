@@ -445,7 +445,7 @@ fast::FastQuant make_fast_quant(double delta)
     return q;
 }
 
-fast::FastGeom make_fast_geometry(const Geometry& g)
+fast::FastGeom make_fast_geometry(const Geometry& g, long long n_frames)
 {
     fast::FastGeom f;
     f.frames = g.frames;
@@ -455,10 +455,29 @@ fast::FastGeom make_fast_geometry(const Geometry& g)
     f.W = g.W;
     f.bw = g.bw;
     f.bpf = g.bpf;
-    f.tiles_per_frame = (g.bpf + fast::kFastBlocksPerCta - 1) / fast::kFastBlocksPerCta;
     f.n = g.n;
+    f.groups_per_frame = (g.bpf + 63) / 64;
+    f.total_groups = n_frames * f.groups_per_frame;
     f.delta32 = g.delta32;
+    f.magic_hi = 0x4B000000u;
     return f;
+}
+
+// persistent grid: one CTA per SM (or fewer when there is not enough work)
+unsigned fast_grid(long long total_groups)
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    const long long want = (total_groups + fast::kFastWarps - 1) / fast::kFastWarps;
+    const long long cap = (long long)sms[dev] * fast::kFastCtasPerSm;
+    return (unsigned)(want < cap ? want : cap);
 }
 
 bool g_force_scalar = false;     // SVS_FORCE_SCALAR=1: route everything through the scalar kernels
@@ -530,15 +549,21 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const fast::FastQuant fq = make_fast_quant(delta);
-    if (fast_enabled() && al && words && delta > 0 && fq.extract_ok) {
+    if (fast_enabled() && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
         fast::FastExtractArgs fa;
-        fa.g = make_fast_geometry(a.g);
+        fa.g = make_fast_geometry(a.g, n_frames);
         fa.q = fq;
         fa.bits = d_bits_out;
         fa.bits_frame_stride = bits_frame_stride;
-        const long long fgrid = n_frames * fa.g.tiles_per_frame;
-        if (channels == 3) fast::extract_fast_kernel<3><<<(unsigned)fgrid, fast::kFastThreads, 0, st>>>(fa);
-        else fast::extract_fast_kernel<1><<<(unsigned)fgrid, fast::kFastThreads, 0, st>>>(fa);
+        const unsigned fgrid = fast_grid(fa.g.total_groups);
+        const bool full = a.g.n == SVS_MAX_AC;
+        if (channels == 3) {
+            if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            else fast::extract_fast_kernel<3, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+        } else {
+            if (full) fast::extract_fast_kernel<1, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            else fast::extract_fast_kernel<1, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+        }
     } else if (channels == 3) { if (al) launch_extract<3, true>(a, words, (unsigned)grid, st); else launch_extract<3, false>(a, words, (unsigned)grid, st); }
     else                      { if (al) launch_extract<1, true>(a, words, (unsigned)grid, st); else launch_extract<1, false>(a, words, (unsigned)grid, st); }
     g_launches.fetch_add(1);
@@ -597,12 +622,13 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     // Frames the payload fills completely go to the packed-FP32 kernel; the frame in which the
     // payload ends and everything after it (and every special case) to the scalar kernel.
     const fast::FastQuant fq = make_fast_quant(delta);
-    if (fast_enabled() && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr) {
+    if (fast_enabled() && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr &&
+        n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
         long long full = payload_total_bits / a.cap;
         if (full > n_frames) full = n_frames;
         if (full > 0) {
             fast::FastEmbedArgs fa;
-            fa.g = make_fast_geometry(a.g);
+            fa.g = make_fast_geometry(a.g, full);
             fa.q = fq;
             fa.payload = a.payload;
             fa.payload_bit_offset = payload_bit_offset;
@@ -612,14 +638,16 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fa.stego_frame_stride = stego_frame_stride;
             fa.stego_row_stride = stego_row_stride;
             fa.bits_embedded = d_bits_embedded_out;
-            const unsigned fgrid = (unsigned)(full * fa.g.tiles_per_frame);
-            if (channels == 3) {
-                if (stego_channels == 1) fast::embed_fast_kernel<3, 1><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-                else fast::embed_fast_kernel<3, 3><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            } else {
-                if (stego_channels == 1) fast::embed_fast_kernel<1, 1><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-                else fast::embed_fast_kernel<1, 3><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            }
+            const unsigned fgrid = fast_grid(fa.g.total_groups);
+            const bool nfull = a.g.n == SVS_MAX_AC;
+#define SVS_LAUNCH_EMBED(CH, OC)                                                                         \
+    do {                                                                                                 \
+        if (nfull) fast::embed_fast_kernel<CH, OC, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);      \
+        else fast::embed_fast_kernel<CH, OC, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);           \
+    } while (0)
+            if (channels == 3) { if (stego_channels == 1) SVS_LAUNCH_EMBED(3, 1); else SVS_LAUNCH_EMBED(3, 3); }
+            else               { if (stego_channels == 1) SVS_LAUNCH_EMBED(1, 1); else SVS_LAUNCH_EMBED(1, 3); }
+#undef SVS_LAUNCH_EMBED
             g_launches.fetch_add(1);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (packed)");

@@ -89,15 +89,31 @@ struct FastQuant {
     int embed_ok, extract_ok;
 };
 
-constexpr int kFastThreads = 128;                 // 4 warps, 64 blocks per warp
-constexpr int kFastBlocksPerCta = 2 * kFastThreads;
+// One CTA per SM, 12 warps, 64 blocks (2 per thread) per warp and per loop iteration.  168
+// registers per thread x 384 threads fills the register file; the CTA is persistent and strides
+// over the (frame, 64-block group) space.
+#ifndef SVS_FAST_THREADS
+#define SVS_FAST_THREADS 384
+#endif
+constexpr int kFastThreads = SVS_FAST_THREADS;
+constexpr int kFastCtasPerSm = 384 / kFastThreads;
+constexpr int kFastWarps = kFastThreads / 32;
+#ifndef SVS_SYNC_LEVEL
+#define SVS_SYNC_LEVEL 1
+#endif
+#define SVS_LOCKSTEP() do { if (SVS_SYNC_LEVEL >= 1) __syncthreads(); } while (0)
+#define SVS_LOCKSTEP2() do { if (SVS_SYNC_LEVEL >= 2) __syncthreads(); } while (0)
+#define SVS_LOCKSTEP3() do { if (SVS_SYNC_LEVEL >= 3) __syncthreads(); } while (0)
 constexpr uint32_t kZone = 4;                     // flagged when fraction bits < kZone (shift = 2 ulp)
 
 struct FastGeom {
     const uint8_t* frames;
     long long frame_stride, row_stride;
-    int H, W, bw, bpf, tiles_per_frame, n;
+    int H, W, bw, bpf, n;
+    int groups_per_frame;                         // ceil(bpf / 64)
+    long long total_groups;                       // n_frames * groups_per_frame
     float delta32;
+    uint32_t magic_hi;                            // 0x4B000000, opaque so that it stays in a register
 };
 
 struct FastEmbedArgs {
@@ -119,41 +135,41 @@ struct FastExtractArgs {
 
 __device__ __forceinline__ uint32_t bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
-// (2^23 + byte SEL of v) as float bits: one PRMT
+// (2^23 + byte SEL of v) as float bits: one PRMT  [v.bSEL, 0x00, 0x00, 0x4B]
 template <int SEL>
-__device__ __forceinline__ uint32_t magic_byte(uint32_t v)
+__device__ __forceinline__ uint32_t magic_byte(uint32_t v, uint32_t magic_hi)
 {
-    return __byte_perm(v, 0x4B000000u, 0x7540 | SEL);      // [v.bSEL, 0x00, 0x00, 0x4B]
+    return __byte_perm(v, magic_hi, 0x7540 | SEL);
 }
 
-// Row r of one block -> 8 "2^23 + gray" float bit patterns.
+// Row of one block -> its 8 gray bytes in two words (BGR: cv2 BGR2GRAY through two dp2a).
 template <int CH>
-__device__ __forceinline__ void load_row_magic(const uint8_t* __restrict__ row, uint32_t (&m)[8])
+__device__ __forceinline__ void load_row_gray(const uint8_t* __restrict__ row, uint32_t& lo, uint32_t& hi)
 {
     if (CH == 1) {
         const uint2 v = __ldg(reinterpret_cast<const uint2*>(row));
-        m[0] = magic_byte<0>(v.x); m[1] = magic_byte<1>(v.x); m[2] = magic_byte<2>(v.x); m[3] = magic_byte<3>(v.x);
-        m[4] = magic_byte<0>(v.y); m[5] = magic_byte<1>(v.y); m[6] = magic_byte<2>(v.y); m[7] = magic_byte<3>(v.y);
+        lo = v.x;
+        hi = v.y;
     } else {
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(row));
         const uint2 b = __ldg(reinterpret_cast<const uint2*>(row) + 1);
         const uint2 c = __ldg(reinterpret_cast<const uint2*>(row) + 2);
         const uint32_t w[7] = {a.x, a.y, b.x, b.y, c.x, c.y, 0u};
+        uint32_t s[8];
 #pragma unroll
         for (int px = 0; px < 8; ++px) {
             const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
             const uint32_t sel = (uint32_t)(off | ((off + 1) << 4) | ((off + 2) << 8) | ((off + 3) << 12));
             const uint32_t bgr = off == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sel);
-            // 2*(3735 B + 19235 G + 9798 R + 16384) < 2^24: gray = bits 16..23 (cv2 BGR2GRAY)
-            uint32_t s = __dp2a_lo((38470u << 16) | 7470u, bgr, 32768u);
-            s = __dp2a_hi(19596u, bgr, s);
-            m[px] = magic_byte<2>(s);
+            // 2*(3735 B + 19235 G + 9798 R + 16384) < 2^24: gray = bits 16..23 of the sum
+            s[px] = __dp2a_hi(19596u, bgr, __dp2a_lo((38470u << 16) | 7470u, bgr, 32768u));
         }
+        lo = __byte_perm(__byte_perm(s[0], s[1], 0x0062), __byte_perm(s[2], s[3], 0x0062), 0x5410);
+        hi = __byte_perm(__byte_perm(s[4], s[5], 0x0062), __byte_perm(s[6], s[7], 0x0062), 0x5410);
     }
 }
 
-// 8 floats of row r of both blocks -> two uint2 of bytes (clip to [0,255], truncate)
-__device__ __forceinline__ uint32_t to_u8(float v)
+__device__ __forceinline__ uint32_t to_u8(float v)      // np.uint8(np.clip(v, 0, 255)): one F2IP
 {
     uint32_t r;
     asm("{.reg .u8 t; cvt.rzi.u8.f32 t, %1; cvt.u32.u8 %0, t;}" : "=r"(r) : "f"(v));
@@ -164,16 +180,20 @@ __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2,
     return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
 
+__device__ __forceinline__ void stg64(uint8_t* p, uint32_t lo, uint32_t hi)
+{
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
+
 template <int OUT_CH>
 __device__ __forceinline__ void store_row(uint8_t* dst, uint32_t lo4, uint32_t hi4)
 {
-    uint2* row = reinterpret_cast<uint2*>(dst);
     if (OUT_CH == 1) {
-        row[0] = make_uint2(lo4, hi4);
+        stg64(dst, lo4, hi4);
     } else {            // gray replicated to B,G,R (cv2.cvtColor GRAY2BGR, embed_process.py:126)
-        row[0] = make_uint2(__byte_perm(lo4, 0, 0x1000), __byte_perm(lo4, 0, 0x2211));
-        row[1] = make_uint2(__byte_perm(lo4, 0, 0x3332), __byte_perm(hi4, 0, 0x1000));
-        row[2] = make_uint2(__byte_perm(hi4, 0, 0x2211), __byte_perm(hi4, 0, 0x3332));
+        stg64(dst, __byte_perm(lo4, 0, 0x1000), __byte_perm(lo4, 0, 0x2211));
+        stg64(dst + 8, __byte_perm(lo4, 0, 0x3332), __byte_perm(hi4, 0, 0x1000));
+        stg64(dst + 16, __byte_perm(hi4, 0, 0x2211), __byte_perm(hi4, 0, 0x3332));
     }
 }
 
@@ -189,233 +209,376 @@ __device__ __forceinline__ void payload_window(const uint32_t* __restrict__ word
     lo = __funnelshift_l(w2, w1, s);
 }
 
-// Exact (reference-order) requantisation of one coefficient: the scalar kernels' formula.
-__device__ __forceinline__ float requant_exact(float c, float d32, uint32_t bit)
+// IEEE-exact c / d from the correctly rounded reciprocal r = RN(1/d): two Newton corrections on
+// the quotient (the sequence __fdiv_rn runs after its own reciprocal; all operands are normal
+// here).  Checked against the FPU division on 2.5e8 (c, d) pairs covering this value range.
+__device__ __forceinline__ float div_exact(float c, float d, float r)
 {
-    const float t = __fdiv_rn(c, d32);
-    const int q = __float2int_rn(t);
-    return __fmul_rn((float)(q - (q & 1) + (int)bit), d32);
+    float q = __fmul_rn(c, r);
+    q = __fmaf_rn(__fmaf_rn(-q, d, c), r, q);
+    return __fmaf_rn(__fmaf_rn(-q, d, c), r, q);
+}
+
+// Rare path, deliberately out of line and looped so that it costs almost no instruction-cache
+// space.  `orig` holds the 8 coefficient pairs of row u before quantisation, `res` the results
+// of the division-free quantiser; every coefficient whose fraction was too close to a rounding
+// boundary is recomputed exactly as the scalar kernels do (IEEE division, round-half-even,
+// float32 product) and patched into `res`.
+__device__ __noinline__ void fix_row_embed(const P2* orig, P2* res, int u, int n, float d32, float r32,
+                                           float r2, float ke, uint32_t emask,
+                                           uint32_t wA0, uint32_t wA1, uint32_t wB0, uint32_t wB1)
+{
+    for (int v = 0; v < 8; ++v) {
+        const int i = 8 * u + v - 1;
+        if (i < 0 || i >= n) continue;
+        float ca, cb, ra, rb;
+        unpkf(orig[v], ca, cb);
+        unpkf(res[v], ra, rb);
+        const uint32_t sh = 31u - (uint32_t)(i & 31);
+        if ((__float_as_uint(__fmaf_rn(ca, r2, ke)) & emask) < kZone) {
+            const int q = __float2int_rn(div_exact(ca, d32, r32));
+            ra = __fmul_rn((float)(q - (q & 1) + (int)(((i < 32 ? wA0 : wA1) >> sh) & 1u)), d32);
+        }
+        if ((__float_as_uint(__fmaf_rn(cb, r2, ke)) & emask) < kZone) {
+            const int q = __float2int_rn(div_exact(cb, d32, r32));
+            rb = __fmul_rn((float)(q - (q & 1) + (int)(((i < 32 ? wB0 : wB1) >> sh) & 1u)), d32);
+        }
+        res[v] = pk(ra, rb);
+    }
+}
+
+// Same for extraction: `rows` = (rowA | rowB << 16), coefficient v at bit 7-v; flagged
+// coefficients get their parity from the exact quotient.
+__device__ __noinline__ uint32_t fix_row_extract(const P2* in, uint32_t rows, int u, int n, float d32, float r32,
+                                                 float kx, uint32_t xmask)
+{
+    for (int v = 0; v < 8; ++v) {
+        const int i = 8 * u + v - 1;
+        if (i < 0 || i >= n) continue;
+        float ca, cb;
+        unpkf(in[v], ca, cb);
+        if ((__float_as_uint(__fmaf_rn(ca, r32, kx)) & xmask) < kZone) {
+            const uint32_t par = (uint32_t)__float2int_rn(div_exact(ca, d32, r32)) & 1u;
+            rows = (rows & ~(0x80u >> v)) | (par << (7 - v));
+        }
+        if ((__float_as_uint(__fmaf_rn(cb, r32, kx)) & xmask) < kZone) {
+            const uint32_t par = (uint32_t)__float2int_rn(div_exact(cb, d32, r32)) & 1u;
+            rows = (rows & ~(0x800000u >> v)) | (par << (23 - v));
+        }
+    }
+    return rows;
+}
+
+// 64-bit pointer += 64-bit stride as two adds that ptxas does not re-derive from a base + offset.
+template <class T>
+__device__ __forceinline__ void step(T*& p, long long stride)
+{
+    asm volatile("add.s64 %0, %0, %1;" : "+l"(p) : "l"(stride));
+}
+
+// Where the 64 blocks of (group g) live, and this lane's two blocks (A = base + lane,
+// B = A + 32, both clamped into the frame; ok* says whether the lane really owns them).
+struct Lane {
+    int f;                       // frame
+    int base, bA, bB;
+    int byA, bxA, byB, bxB;
+    bool okA, okB;
+};
+__device__ __forceinline__ Lane locate(const FastGeom& G, long long g, int lane)
+{
+    Lane L;
+    const unsigned gi = (unsigned)g;                       // total_groups < 2^31 (host-checked)
+    const unsigned f = gi / (unsigned)G.groups_per_frame;
+    L.f = (int)f;
+    L.base = (int)(gi - f * (unsigned)G.groups_per_frame) * 64;
+    const int last = G.bpf - 1;
+    L.okA = L.base + lane <= last;
+    L.okB = L.base + 32 + lane <= last;
+    L.bA = min(L.base + lane, last);
+    L.bB = min(L.base + 32 + lane, last);
+    L.byA = (int)((unsigned)L.bA / (unsigned)G.bw);
+    L.bxA = L.bA - L.byA * G.bw;
+    if (G.bw >= 32 && L.okB) {                             // B is 32 blocks further along the raster
+        L.bxB = L.bxA + 32;
+        L.byB = L.byA;
+        if (L.bxB >= G.bw) { L.bxB -= G.bw; L.byB += 1; }
+    } else {
+        L.byB = (int)((unsigned)L.bB / (unsigned)G.bw);
+        L.bxB = L.bB - L.byB * G.bw;
+    }
+    return L;
+}
+
+template <int CH>
+__device__ __forceinline__ void prefetch_group(const FastGeom& G, long long g, int lane)
+{
+    if (g >= G.total_groups) return;
+    const Lane L = locate(G, g, lane);
+    const uint8_t* frame = G.frames + L.f * G.frame_stride;
+    const uint8_t* pA = frame + (long long)(L.byA * 8) * G.row_stride + L.bxA * (8 * CH);
+    const uint8_t* pB = frame + (long long)(L.byB * 8) * G.row_stride + L.bxB * (8 * CH);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pA));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pB));
+        step(pA, G.row_stride);
+        step(pB, G.row_stride);
+    }
+}
+#ifdef SVS_L2_PREFETCH          // measured: no gain on B200 (2.24 ms vs 2.20 ms per 600 frames), off by default
+#define SVS_PREFETCH(CH, G, g, lane) prefetch_group<CH>(G, g, lane)
+#else
+#define SVS_PREFETCH(CH, G, g, lane) ((void)0)
+#endif
+
+// Loads both blocks of this lane as packed gray bytes (g[2r], g[2r+1] = row r).
+template <int CH>
+__device__ __forceinline__ void load_blocks_gray(const FastGeom& G, const Lane& L, uint32_t (&gA)[16], uint32_t (&gB)[16])
+{
+    const uint8_t* frame = G.frames + L.f * G.frame_stride;
+    const uint8_t* pA = frame + (long long)(L.byA * 8) * G.row_stride + L.bxA * (8 * CH);
+    const uint8_t* pB = frame + (long long)(L.byB * 8) * G.row_stride + L.bxB * (8 * CH);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        load_row_gray<CH>(pA, gA[2 * r], gA[2 * r + 1]);
+        load_row_gray<CH>(pB, gB[2 * r], gB[2 * r + 1]);
+        step(pA, G.row_stride);
+        step(pB, G.row_stride);
+    }
+}
+
+// Column c of both blocks -> 8 packed floats, then the axis-0 transform of that column; written
+// column by column so that the byte->float work (ALU pipe) of column c+1 can overlap the FP32
+// work of column c inside one warp.
+template <int C>
+__device__ __forceinline__ void column_fwd(const PackedOps& ops, const uint32_t (&gA)[16], const uint32_t (&gB)[16],
+                                           uint32_t magic_hi, P2 (&x)[64])
+{
+    const P2 unbias = pk(-8388608.0f, -8388608.0f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        x[r * 8 + C] = add2(pku(magic_byte<(C & 3)>(gA[2 * r + (C >> 2)], magic_hi),
+                                magic_byte<(C & 3)>(gB[2 * r + (C >> 2)], magic_hi)), unbias);      // exact
+    svs::dct8_fwd<8>(ops, x + C);
 }
 
 // ------------------------------------------------------------------------------------------
 // embed: every block of every frame handled here is completely filled with payload (k == n)
 // ------------------------------------------------------------------------------------------
-template <int CH, int OUT_CH>
-__global__ void __launch_bounds__(kFastThreads, 3) embed_fast_kernel(const FastEmbedArgs a)
+template <int CH, int OUT_CH, bool NFULL>
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kernel(const FastEmbedArgs a)
 {
     const FastGeom& G = a.g;
-    const long long f = blockIdx.x / G.tiles_per_frame;
-    const int tile = (int)(blockIdx.x - f * G.tiles_per_frame);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = tile * kFastBlocksPerCta + warp * 64;
-    if (base >= G.bpf) return;
-    if (base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[f] = a.cap;
-
-    const int last = G.bpf - 1;
-    const int bA = min(base + lane, last), bB = min(base + 32 + lane, last);
-    const bool okA = base + lane <= last, okB = base + 32 + lane <= last;
-    const int byA = bA / G.bw, bxA = bA - byA * G.bw;
-    const int byB = bB / G.bw, bxB = bB - byB * G.bw;
-    const uint8_t* frame = G.frames + f * G.frame_stride;
-    const uint8_t* srcA = frame + (long long)(byA * 8) * G.row_stride + (long long)bxA * (8 * CH);
-    const uint8_t* srcB = frame + (long long)(byB * 8) * G.row_stride + (long long)bxB * (8 * CH);
-
+    const int n = NFULL ? 63 : G.n;
     PackedOps ops;
     ops.negzero = pk(a.q.negzero, a.q.negzero);
-    P2 x[64];
-    {
-        const P2 unbias = pk(-8388608.0f, -8388608.0f);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t mA[8], mB[8];
-            load_row_magic<CH>(srcA + r * G.row_stride, mA);
-            load_row_magic<CH>(srcB + r * G.row_stride, mB);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[r * 8 + c] = add2(pku(mA[c], mB[c]), unbias);   // exact
-        }
-    }
-    svs::dct2_fwd(ops, x);
-
-    // payload windows of the two blocks: coefficient i reads bit i (MSB first)
-    uint32_t wA[2], wB[2];
-    {
-        const long long at = a.payload_bit_offset + f * a.cap;
-        payload_window(a.payload, a.payload_last_word, at + (long long)bA * G.n, wA[0], wA[1]);
-        payload_window(a.payload, a.payload_last_word, at + (long long)bB * G.n, wB[0], wB[1]);
-    }
-    const int n = G.n;
     const P2 r2 = pk(a.q.r2, a.q.r2), ke = pk(a.q.ke, a.q.ke), d2 = pk(a.q.d2, a.q.d2), k0 = pk(a.q.k0, a.q.k0);
     const uint32_t emask = a.q.emask, ebit = a.q.ebit;
     const int erot = a.q.erot;
+
+    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += (long long)gridDim.x * kFastWarps) {
+        SVS_LOCKSTEP();                        // keep the warps of the CTA in one instruction-cache window
+        long long g = g0 + warp;
+        const bool live = g < G.total_groups;          // idle warps redo the last group, stores masked
+        if (!live) g = G.total_groups - 1;
+        Lane L = locate(G, g, lane);
+        if (!live) { L.okA = false; L.okB = false; }
+        SVS_PREFETCH(CH, G, g + (long long)gridDim.x * kFastWarps, lane);
+        if (live && L.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[L.f] = a.cap;
+
+        P2 x[64];
+        {
+            uint32_t gA[16], gB[16];
+            load_blocks_gray<CH>(G, L, gA, gB);
+            column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<6>(ops, gA, gB, G.magic_hi, x); column_fwd<7>(ops, gA, gB, G.magic_hi, x);
+        }
+        SVS_LOCKSTEP2();
+
+        // payload windows of the two blocks: coefficient i reads bit i (MSB first).  The words are
+        // pre-rotated once so that bit i sits `i` places below position erot: bringing it there
+        // is then a rotate by the compile-time constant i.
+        uint32_t wA[2], wB[2], pA[2], pB[2];
+        {
+            const long long at = a.payload_bit_offset + L.f * a.cap;
+            payload_window(a.payload, a.payload_last_word, at + (long long)L.bA * n, wA[0], wA[1]);
+            payload_window(a.payload, a.payload_last_word, at + (long long)L.bB * n, wB[0], wB[1]);
+            const int pre = (erot - 31) & 31;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if (8 * u - 1 < n) {                                  // uniform: row u holds indices 8u-1 .. 8u+6
-            uint32_t worst = 0xffffffffu;
-            P2 keep[8];
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const int i = 8 * u + v - 1;                  // payload bit / coefficient number
-                keep[v] = x[8 * u + v];
-                if (i >= 0 && i < n) {
-                    const P2 y = fma2(x[8 * u + v], r2, ke);
-                    uint32_t ya, yb;
-                    unpk(y, ya, yb);
-                    const uint32_t la = ya & emask, lb = yb & emask;
-                    worst = min(worst, min(la, lb));
-                    // rotate payload bit i (bit 31-(i&31) of its word) to position erot
-                    const int rot = (erot - (31 - (i & 31))) & 31;
-                    const uint32_t ta = __funnelshift_l(wA[i >> 5], wA[i >> 5], rot) & ebit;
-                    const uint32_t tb = __funnelshift_l(wB[i >> 5], wB[i >> 5], rot) & ebit;
-                    // M + floor() + bit/2, then (2e + bit) * delta in one rounding
-                    x[8 * u + v] = fma2(pku((ya & ~emask) | ta, (yb & ~emask) | tb), d2, k0);
-                }
+            for (int j = 0; j < 2; ++j) {
+                pA[j] = __funnelshift_l(wA[j], wA[j], pre);
+                pB[j] = __funnelshift_l(wB[j], wB[j], pre);
             }
-            if (worst < kZone) {                              // rare: a fraction too close to call
+        }
+
+        // axis-1 transform of row u, then its quantisation (FP32 and ALU work interleave)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            svs::dct8_fwd<1>(ops, x + 8 * u);
+            if (NFULL || 8 * u - 1 < n) {
+                uint32_t worst = 0xffffffffu;
+                P2 nx[8];
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
-                    const int i = 8 * u + v - 1;
-                    if (i >= 0 && i < n) {
-                        float ca, cb;
-                        unpkf(keep[v], ca, cb);
-                        const uint32_t bitA = (wA[i >> 5] >> (31 - (i & 31))) & 1u;
-                        const uint32_t bitB = (wB[i >> 5] >> (31 - (i & 31))) & 1u;
-                        x[8 * u + v] = pk(requant_exact(ca, G.delta32, bitA), requant_exact(cb, G.delta32, bitB));
+                    const int i = 8 * u + v - 1;                  // payload bit / coefficient number
+                    nx[v] = x[8 * u + v];
+                    if (i >= 0 && (NFULL || i < n)) {
+                        const P2 y = fma2(x[8 * u + v], r2, ke);
+                        uint32_t ya, yb;
+                        unpk(y, ya, yb);
+                        worst = min(worst, min(ya & emask, yb & emask));
+                        const uint32_t ta = __funnelshift_l(pA[i >> 5], pA[i >> 5], i & 31) & ebit;
+                        const uint32_t tb = __funnelshift_l(pB[i >> 5], pB[i >> 5], i & 31) & ebit;
+                        // M + floor() + bit/2, then (2e + bit) * delta in one rounding
+                        nx[v] = fma2(pku((ya & ~emask) | ta, (yb & ~emask) | tb), d2, k0);
                     }
                 }
+                if (worst < kZone) {                              // rare: a fraction too close to call
+                    P2 orig[8], res[8];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) { orig[v] = x[8 * u + v]; res[v] = nx[v]; }
+                    fix_row_embed(orig, res, u, n, G.delta32, a.q.r, a.q.r2, a.q.ke, emask, wA[0], wA[1], wB[0], wB[1]);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) nx[v] = res[v];
+                }
+#pragma unroll
+                for (int v = 0; v < 8; ++v) x[8 * u + v] = nx[v];
             }
+            if (u == 3) SVS_LOCKSTEP3();
         }
-    }
-    svs::dct2_inv(ops, x);
+        SVS_LOCKSTEP2();
 
-    uint8_t* out = a.stego + f * a.stego_frame_stride;
-    uint8_t* dstA = out + (long long)(byA * 8) * a.stego_row_stride + (long long)bxA * (8 * OUT_CH);
-    uint8_t* dstB = out + (long long)(byB * 8) * a.stego_row_stride + (long long)bxB * (8 * OUT_CH);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        uint32_t ba[8], bb[8];
+        for (int v = 0; v < 8; ++v) svs::dct8_inv<8>(ops, x + v);
+
+        SVS_LOCKSTEP2();
+        uint8_t* out = a.stego + L.f * a.stego_frame_stride;
+        uint8_t* dstA = out + (long long)(L.byA * 8) * a.stego_row_stride + L.bxA * (8 * OUT_CH);
+        uint8_t* dstB = out + (long long)(L.byB * 8) * a.stego_row_stride + L.bxB * (8 * OUT_CH);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float va, vb;
-            unpkf(x[r * 8 + c], va, vb);
-            ba[c] = to_u8(va);
-            bb[c] = to_u8(vb);
+        for (int r = 0; r < 8; ++r) {
+            svs::dct8_inv<1>(ops, x + 8 * r);
+            uint32_t ba[8], bb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float va, vb;
+                unpkf(x[r * 8 + c], va, vb);
+                ba[c] = to_u8(va);
+                bb[c] = to_u8(vb);
+            }
+            const uint32_t a0 = pack4(ba[0], ba[1], ba[2], ba[3]), a1 = pack4(ba[4], ba[5], ba[6], ba[7]);
+            const uint32_t b0 = pack4(bb[0], bb[1], bb[2], bb[3]), b1 = pack4(bb[4], bb[5], bb[6], bb[7]);
+            if (L.okA) store_row<OUT_CH>(dstA, a0, a1);
+            if (L.okB) store_row<OUT_CH>(dstB, b0, b1);
+            step(dstA, a.stego_row_stride);
+            step(dstB, a.stego_row_stride);
+            if (r == 3) SVS_LOCKSTEP3();
         }
-        if (okA) store_row<OUT_CH>(dstA + r * a.stego_row_stride, pack4(ba[0], ba[1], ba[2], ba[3]), pack4(ba[4], ba[5], ba[6], ba[7]));
-        if (okB) store_row<OUT_CH>(dstB + r * a.stego_row_stride, pack4(bb[0], bb[1], bb[2], bb[3]), pack4(bb[4], bb[5], bb[6], bb[7]));
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // extract
 // ------------------------------------------------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(kFastThreads, 3) extract_fast_kernel(const FastExtractArgs a)
+template <int CH, bool NFULL>
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_kernel(const FastExtractArgs a)
 {
-    __shared__ uint32_t pack[kFastThreads / 32][128];
+    __shared__ uint32_t pack[kFastWarps][128];
     const FastGeom& G = a.g;
-    const long long f = blockIdx.x / G.tiles_per_frame;
-    const int tile = (int)(blockIdx.x - f * G.tiles_per_frame);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = tile * kFastBlocksPerCta + warp * 64;
-    if (base >= G.bpf) return;
-    const int n = G.n;
-
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
-    __syncwarp();
-
-    const int last = G.bpf - 1;
-    const int bA = min(base + lane, last), bB = min(base + 32 + lane, last);
-    const bool okA = base + lane <= last, okB = base + 32 + lane <= last;
-    const int byA = bA / G.bw, bxA = bA - byA * G.bw;
-    const int byB = bB / G.bw, bxB = bB - byB * G.bw;
-    const uint8_t* frame = G.frames + f * G.frame_stride;
-    const uint8_t* srcA = frame + (long long)(byA * 8) * G.row_stride + (long long)bxA * (8 * CH);
-    const uint8_t* srcB = frame + (long long)(byB * 8) * G.row_stride + (long long)bxB * (8 * CH);
-
+    const int n = NFULL ? 63 : G.n;
     PackedOps ops;
     ops.negzero = pk(a.q.negzero, a.q.negzero);
-    P2 x[64];
-    {
-        const P2 unbias = pk(-8388608.0f, -8388608.0f);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            uint32_t mA[8], mB[8];
-            load_row_magic<CH>(srcA + r * G.row_stride, mA);
-            load_row_magic<CH>(srcB + r * G.row_stride, mB);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[r * 8 + c] = add2(pku(mA[c], mB[c]), unbias);
-        }
-    }
-    svs::dct2_fwd(ops, x);
-
     const P2 rr = pk(a.q.r, a.q.r), kx = pk(a.q.kx, a.q.kx);
     const uint32_t xmask = a.q.xmask;
     const int xk = a.q.xk;
-    uint32_t hiA = 0, loA = 0, hiB = 0, loB = 0;            // bit i at (hi:lo) bit 63-i
+
+    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += (long long)gridDim.x * kFastWarps) {
+        SVS_LOCKSTEP();
+        long long g = g0 + warp;
+        const bool live = g < G.total_groups;
+        if (!live) g = G.total_groups - 1;
+        Lane L = locate(G, g, lane);
+        if (!live) { L.okA = false; L.okB = false; }
+        SVS_PREFETCH(CH, G, g + (long long)gridDim.x * kFastWarps, lane);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if (8 * u - 1 < n) {
-            uint32_t worst = 0xffffffffu;
-            uint32_t rowA = 0, rowB = 0;                     // coefficient v of this row at bit 7-v
+        for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
+
+        P2 x[64];
+        {
+            uint32_t gA[16], gB[16];
+            load_blocks_gray<CH>(G, L, gA, gB);
+            column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<6>(ops, gA, gB, G.magic_hi, x); column_fwd<7>(ops, gA, gB, G.magic_hi, x);
+        }
+        SVS_LOCKSTEP2();
+
+        uint32_t hiA = 0, loA = 0, hiB = 0, loB = 0;            // bit i at (hi:lo) bit 63-i
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const int i = 8 * u + v - 1;
-                if (i >= 0 && i < n) {
-                    const P2 y = fma2(x[8 * u + v], rr, kx);
-                    uint32_t ya, yb;
-                    unpk(y, ya, yb);
-                    worst = min(worst, min(ya & xmask, yb & xmask));
-                    // parity (bit xk) -> bit 7-v
-                    const int rot = (7 - v - xk) & 31;
-                    rowA |= __funnelshift_l(ya, ya, rot) & (0x80u >> v);
-                    rowB |= __funnelshift_l(yb, yb, rot) & (0x80u >> v);
-                }
-            }
-            if (worst < kZone) {
-                rowA = 0;
-                rowB = 0;
+        for (int u = 0; u < 8; ++u) {
+            if (NFULL || 8 * u - 1 < n) {
+                svs::dct8_fwd<1>(ops, x + 8 * u);
+                uint32_t worst = 0xffffffffu;
+                uint32_t rowA = 0, rowB = 0;                     // coefficient v of this row at bit 7-v
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
                     const int i = 8 * u + v - 1;
-                    if (i >= 0 && i < n) {
-                        float ca, cb;
-                        unpkf(x[8 * u + v], ca, cb);
-                        rowA |= ((uint32_t)__float2int_rn(__fdiv_rn(ca, G.delta32)) & 1u) << (7 - v);
-                        rowB |= ((uint32_t)__float2int_rn(__fdiv_rn(cb, G.delta32)) & 1u) << (7 - v);
+                    if (i >= 0 && (NFULL || i < n)) {
+                        const P2 y = fma2(x[8 * u + v], rr, kx);
+                        uint32_t ya, yb;
+                        unpk(y, ya, yb);
+                        worst = min(worst, min(ya & xmask, yb & xmask));
+                        const int rot = (7 - v - xk) & 31;       // parity (bit xk) -> bit 7-v
+                        rowA |= __funnelshift_l(ya, ya, rot) & (0x80u >> v);
+                        rowB |= __funnelshift_l(yb, yb, rot) & (0x80u >> v);
                     }
                 }
-            }
-            // row u covers stream bits 8u-1 .. 8u+6 of the block: bit 7-v of row -> stream bit 8u+v-1
-            if (u == 0)      { hiA |= rowA << 25; hiB |= rowB << 25; }            // v=1..7 -> bits 0..6
-            else if (u < 4)  { hiA |= rowA << (25 - 8 * u); hiB |= rowB << (25 - 8 * u); }
-            else if (u == 4) { hiA |= rowA >> 7; loA |= rowA << 25; hiB |= rowB >> 7; loB |= rowB << 25; }
-            else             { loA |= rowA << (57 - 8 * u); loB |= rowB << (57 - 8 * u); }
-        }
-    }
-    if (!okA) { hiA = 0; loA = 0; }
-    if (!okB) { hiB = 0; loB = 0; }
-    {
-        // place the two n-bit strings at bit offsets lane*n and (32+lane)*n of the warp's run
-        uint32_t* p = pack[warp];
-        uint32_t o = (uint32_t)lane * (uint32_t)n, w0 = o >> 5, sh = o & 31;
-        uint32_t p0 = hiA >> sh, p1 = __funnelshift_r(loA, hiA, sh), p2 = __funnelshift_r(0u, loA, sh);
-        if (p0) atomicOr(p + w0, p0);
-        if (p1) atomicOr(p + w0 + 1, p1);
-        if (p2) atomicOr(p + w0 + 2, p2);
-        o = (uint32_t)(32 + lane) * (uint32_t)n; w0 = o >> 5; sh = o & 31;
-        p0 = hiB >> sh; p1 = __funnelshift_r(loB, hiB, sh); p2 = __funnelshift_r(0u, loB, sh);
-        if (p0) atomicOr(p + w0, p0);
-        if (p1) atomicOr(p + w0 + 1, p1);
-        if (p2) atomicOr(p + w0 + 2, p2);
-    }
-    __syncwarp();
-    const int nblk = min(64, G.bpf - base);
-    const int nwords = (nblk * n + 31) >> 5;
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + f * a.bits_frame_stride + (long long)(base >> 5) * (4 * n));
+                if (worst < kZone) {
+                    P2 in[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (lane + 32 * j < nwords) o32[lane + 32 * j] = bswap(pack[warp][lane + 32 * j]);
+                    for (int v = 0; v < 8; ++v) in[v] = x[8 * u + v];
+                    const uint32_t both = fix_row_extract(in, rowA | (rowB << 16), u, n, G.delta32, a.q.r, a.q.kx, xmask);
+                    rowA = both & 0xffu;
+                    rowB = both >> 16;
+                }
+                // bit 7-v of the row -> stream bit 8u+v-1 of the block -> (hi:lo) bit 64-8u-v
+                if (u == 0)      { hiA |= rowA << 25; hiB |= rowB << 25; }
+                else if (u < 4)  { hiA |= rowA << (25 - 8 * u); hiB |= rowB << (25 - 8 * u); }
+                else if (u == 4) { hiA |= rowA >> 7; loA |= rowA << 25; hiB |= rowB >> 7; loB |= rowB << 25; }
+                else             { loA |= rowA << (57 - 8 * u); loB |= rowB << (57 - 8 * u); }
+            }
+        }
+        if (!L.okA) { hiA = 0; loA = 0; }
+        if (!L.okB) { hiB = 0; loB = 0; }
+        __syncwarp();
+        {
+            // place the two n-bit strings at bit offsets lane*n and (32+lane)*n of the warp's run
+            uint32_t* p = pack[warp];
+            uint32_t o = (uint32_t)lane * (uint32_t)n, w0 = o >> 5, sh = o & 31;
+            uint32_t p0 = hiA >> sh, p1 = __funnelshift_r(loA, hiA, sh), p2 = __funnelshift_r(0u, loA, sh);
+            if (p0) atomicOr(p + w0, p0);
+            if (p1) atomicOr(p + w0 + 1, p1);
+            if (p2) atomicOr(p + w0 + 2, p2);
+            o = (uint32_t)(32 + lane) * (uint32_t)n; w0 = o >> 5; sh = o & 31;
+            p0 = hiB >> sh; p1 = __funnelshift_r(loB, hiB, sh); p2 = __funnelshift_r(0u, loB, sh);
+            if (p0) atomicOr(p + w0, p0);
+            if (p1) atomicOr(p + w0 + 1, p1);
+            if (p2) atomicOr(p + w0 + 2, p2);
+        }
+        __syncwarp();
+        const int nblk = live ? min(64, G.bpf - L.base) : 0;
+        const int nwords = (nblk * n + 31) >> 5;
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + L.f * a.bits_frame_stride + (long long)(L.base >> 5) * (4 * n));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < nwords) o32[lane + 32 * j] = bswap(pack[warp][lane + 32 * j]);
+        __syncwarp();
+    }
 }
 
 }  // namespace fast
