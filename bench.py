@@ -110,13 +110,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------
-def _port_round_trip(seed):
-    """One 1080p/63 round trip through the loop-structured port of the reference (one process)."""
+def _port_round_trip(job):
+    """One 1080p/63 round trip (or the top `rows` pixel rows of one) through the loop-structured
+    port of the reference, in one process."""
+    seed, rows = job
     import numpy as np
     from oracle import ref_port
     from tests.synth import synth_frames, synth_bits, bits_to_str
-    frame = synth_frames("cpu%d" % seed, (H, W, CH), LO, HI)
-    cap = (H // 8) * (W // 8) * NUM_AC
+    frame = synth_frames("cpu%d" % seed, (H, W, CH), LO, HI)[:rows]
+    cap = (rows // 8) * (W // 8) * NUM_AC
     seg = bits_to_str(synth_bits("cpu%d" % seed, cap))
     t0 = time.perf_counter()
     _, stego, k = ref_port.proses_frame_qim_dct(frame, 'embed', DELTA, seg, num_ac_coeffs_to_use=NUM_AC)
@@ -126,24 +128,28 @@ def _port_round_trip(seed):
     return dt
 
 
-def cpu_port_baseline(frames_per_proc=1, max_procs=None):
-    """Reference-structured CPU path on all host cores: one process per core, disjoint frames."""
+def cpu_port_baseline(rows=H, pool=None, step=0):
+    """Reference-structured CPU path on all host cores: one process per core, disjoint frames
+    (`rows` < 1080 times a strip of each frame; the per-block cost does not depend on the strip)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    if max_procs:
-        cores = min(cores, max_procs)
-    ctx = mp.get_context("spawn")
-    jobs = list(range(cores * frames_per_proc))
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        per = pool.map(_port_round_trip, jobs)
-    wall = time.perf_counter() - t0
-    busy = max(per) * frames_per_proc
-    return {"value": len(jobs) / busy, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d frames (1 per process x %d processes) of the 1080p/63-AC/delta-20 round trip through "
-                      "oracle/ref_port.py (per-block scipy.fftpack + per-coefficient round(), the reference's own "
-                      "loop structure); rate = frames / slowest process time; pool wall %.1fs" % (len(jobs), cores, wall),
-            "per_core_frames_per_s": 1.0 / statistics.mean(per)}
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        t0 = time.perf_counter()
+        per = pool.map(_port_round_trip, [(step * cores + i, rows) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    frac = rows / float(H)
+    return {"value": cores * frac / max(per), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d processes x %d of 1080 pixel rows of one 1080p/63-AC/delta-20 frame each, embed+extract "
+                      "through oracle/ref_port.py (per-block scipy.fftpack + per-coefficient round(), the "
+                      "reference's own loop structure); rate = frames / slowest process; wall %.1fs" % (cores, rows, wall),
+            "per_core_frames_per_s": frac / statistics.mean(per)}
 
 
 def cpu_c_oracle_rate(frames=32):
@@ -164,20 +170,36 @@ def cpu_c_oracle_rate(frames=32):
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+
+    A step is a bounded sample of the workload: every host core runs the top `rows` pixel rows of
+    one 1080p frame; `rows` is chosen so that warmup + steps fit SVS_REF_BUDGET_S (default 150 s)."""
     if rank != 0:
         return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    budget = float(os.environ.get("SVS_REF_BUDGET_S", "150"))
+    per_frame_s = 6.0                                   # one 1080p/63 round trip per core, measured ~4.7 s
+    n = max(1, args.warmup + args.steps)
+    rows = int(H * min(1.0, budget / n / per_frame_s)) // 8 * 8
+    rows = max(8, min(H, rows))
     vals, last = [], None
-    for i in range(args.warmup + args.steps):
-        last = cpu_port_baseline(frames_per_proc=1)
-        if i >= args.warmup:
-            vals.append(last["value"])
+    pool = mp.get_context("spawn").Pool(cores)
+    try:
+        for i in range(args.warmup + args.steps):
+            last = cpu_port_baseline(rows=rows, pool=pool, step=i)
+            if i >= args.warmup:
+                vals.append(last["value"])
+    finally:
+        pool.close()
+        pool.join()
     v = statistics.mean(vals)
     last["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * last["cores"] / v,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * cores * rows / H / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "step": "one 1080p round trip per host core (bounded sample)"},
+            "config": {"workload": workload_name(),
+                       "step": "bounded sample: %d of 1080 pixel rows of one frame per host core" % rows},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -335,7 +357,7 @@ def main():
     }
     if world == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_port_baseline(frames_per_proc=1)
+            line["cpu_baseline"] = cpu_port_baseline()
             line["cpu_baseline_c_oracle"] = cpu_c_oracle_rate()
         except Exception as exc:                       # the GPU numbers stay valid without it
             line["cpu_baseline"] = {"error": repr(exc)}
