@@ -131,9 +131,11 @@ int svs_embed_frames_host(svs_ctx* ctx, const uint8_t* h_frames, int channels, i
 /* Number of kernels this library has launched in the calling process (for bench accounting). */
 int64_t svs_kernel_launch_count(void);
 
-/* Diagnostic: on=1 routes every call through the scalar one-block-per-thread kernels, on=0
- * re-enables the packed-FP32 kernels (default), on<0 only queries.  Returns the previous
- * setting.  Both kernel families produce identical results; the tests use this to prove it. */
+/* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 "tile" kernels
+ * whenever they apply, scalar kernels otherwise), 1 = scalar one-block-per-thread kernels only,
+ * 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh); negative
+ * only queries.  Returns the previous setting.  All families produce identical results; the
+ * tests use this to prove it.  Environment variable SVS_KERNEL_FAMILY sets the default. */
 int svs_debug_force_scalar(int on);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@
 #include "svs_b200.h"
 #include "svs_math.cuh"
 #include "svs_fast.cuh"
+#include "svs_tile.cuh"
 
 namespace {
 
@@ -480,16 +481,55 @@ unsigned fast_grid(long long total_groups)
     return (unsigned)(want < cap ? want : cap);
 }
 
-bool g_force_scalar = false;     // SVS_FORCE_SCALAR=1: route everything through the scalar kernels
+// Kernel family: 0 = automatic (packed "tile" kernels when applicable), 1 = scalar only,
+// 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh).
+int g_family = 0;
 
-bool fast_enabled()
+int family()
 {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("SVS_FORCE_SCALAR");
-        cached = (e && e[0] == '1') ? 0 : 1;
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SVS_KERNEL_FAMILY");
+        env = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
     }
-    return cached == 1 && !g_force_scalar;
+    return g_family != 0 ? g_family : env;
+}
+
+unsigned tile_grid(long long total_groups)
+{
+    const unsigned sm_ctas = fast_grid(1ll << 40) * tile::kTileCtasPerSm / fast::kFastCtasPerSm;
+    const long long want = (total_groups + tile::kTileWarps - 1) / tile::kTileWarps;
+    return (unsigned)(want < sm_ctas ? want : sm_ctas);
+}
+
+template <int CH, int OC, bool NFULL>
+cudaError_t launch_tile_embed(const fast::FastEmbedArgs& fa, cudaStream_t st)
+{
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(tile::embed_tile_kernel<CH, OC, NFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::kTileSmemBytes);
+        if (e != cudaSuccess) return e;
+        ready[dev] = true;
+    }
+    tile::embed_tile_kernel<CH, OC, NFULL><<<tile_grid(fa.g.total_groups), tile::kTileThreads, tile::kTileSmemBytes, st>>>(fa);
+    return cudaGetLastError();
+}
+
+template <int CH, bool NFULL>
+cudaError_t launch_tile_extract(const fast::FastExtractArgs& fa, cudaStream_t st)
+{
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(tile::extract_tile_kernel<CH, NFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::kTileSmemBytes);
+        if (e != cudaSuccess) return e;
+        ready[dev] = true;
+    }
+    tile::extract_tile_kernel<CH, NFULL><<<tile_grid(fa.g.total_groups), tile::kTileThreads, tile::kTileSmemBytes, st>>>(fa);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -507,8 +547,8 @@ int64_t svs_kernel_launch_count(void) { return g_launches.load(); }
 
 int svs_debug_force_scalar(int on)
 {
-    const int prev = g_force_scalar ? 1 : 0;
-    if (on >= 0) g_force_scalar = on != 0;
+    const int prev = g_family;
+    if (on >= 0 && on <= 3) g_family = on;
     return prev;
 }
 
@@ -549,21 +589,30 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const fast::FastQuant fq = make_fast_quant(delta);
-    if (fast_enabled() && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
+    if (family() != 1 && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
         fast::FastExtractArgs fa;
         fa.g = make_fast_geometry(a.g, n_frames);
         fa.q = fq;
         fa.bits = d_bits_out;
         fa.bits_frame_stride = bits_frame_stride;
-        const unsigned fgrid = fast_grid(fa.g.total_groups);
         const bool full = a.g.n == SVS_MAX_AC;
-        if (channels == 3) {
-            if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            else fast::extract_fast_kernel<3, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+        cudaError_t fe;
+        if (family() == 2) {
+            const unsigned fgrid = fast_grid(fa.g.total_groups);
+            if (channels == 3) {
+                if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                else fast::extract_fast_kernel<3, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            } else {
+                if (full) fast::extract_fast_kernel<1, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                else fast::extract_fast_kernel<1, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            }
+            fe = cudaGetLastError();
+        } else if (channels == 3) {
+            fe = full ? launch_tile_extract<3, true>(fa, st) : launch_tile_extract<3, false>(fa, st);
         } else {
-            if (full) fast::extract_fast_kernel<1, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            else fast::extract_fast_kernel<1, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+            fe = full ? launch_tile_extract<1, true>(fa, st) : launch_tile_extract<1, false>(fa, st);
         }
+        if (fe != cudaSuccess) return cuda_fail(fe, "svs_extract_frames launch (packed)");
     } else if (channels == 3) { if (al) launch_extract<3, true>(a, words, (unsigned)grid, st); else launch_extract<3, false>(a, words, (unsigned)grid, st); }
     else                      { if (al) launch_extract<1, true>(a, words, (unsigned)grid, st); else launch_extract<1, false>(a, words, (unsigned)grid, st); }
     g_launches.fetch_add(1);
@@ -622,7 +671,7 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     // Frames the payload fills completely go to the packed-FP32 kernel; the frame in which the
     // payload ends and everything after it (and every special case) to the scalar kernel.
     const fast::FastQuant fq = make_fast_quant(delta);
-    if (fast_enabled() && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr &&
+    if (family() != 1 && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr &&
         n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
         long long full = payload_total_bits / a.cap;
         if (full > n_frames) full = n_frames;
@@ -638,16 +687,28 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fa.stego_frame_stride = stego_frame_stride;
             fa.stego_row_stride = stego_row_stride;
             fa.bits_embedded = d_bits_embedded_out;
-            const unsigned fgrid = fast_grid(fa.g.total_groups);
             const bool nfull = a.g.n == SVS_MAX_AC;
+            if (family() == 2) {
+                const unsigned fgrid = fast_grid(fa.g.total_groups);
 #define SVS_LAUNCH_EMBED(CH, OC)                                                                         \
     do {                                                                                                 \
         if (nfull) fast::embed_fast_kernel<CH, OC, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);      \
         else fast::embed_fast_kernel<CH, OC, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);           \
     } while (0)
-            if (channels == 3) { if (stego_channels == 1) SVS_LAUNCH_EMBED(3, 1); else SVS_LAUNCH_EMBED(3, 3); }
-            else               { if (stego_channels == 1) SVS_LAUNCH_EMBED(1, 1); else SVS_LAUNCH_EMBED(1, 3); }
+                if (channels == 3) { if (stego_channels == 1) SVS_LAUNCH_EMBED(3, 1); else SVS_LAUNCH_EMBED(3, 3); }
+                else               { if (stego_channels == 1) SVS_LAUNCH_EMBED(1, 1); else SVS_LAUNCH_EMBED(1, 3); }
 #undef SVS_LAUNCH_EMBED
+            } else {
+                cudaError_t fe;
+                if (channels == 3) {
+                    if (stego_channels == 1) fe = nfull ? launch_tile_embed<3, 1, true>(fa, st) : launch_tile_embed<3, 1, false>(fa, st);
+                    else                     fe = nfull ? launch_tile_embed<3, 3, true>(fa, st) : launch_tile_embed<3, 3, false>(fa, st);
+                } else {
+                    if (stego_channels == 1) fe = nfull ? launch_tile_embed<1, 1, true>(fa, st) : launch_tile_embed<1, 1, false>(fa, st);
+                    else                     fe = nfull ? launch_tile_embed<1, 3, true>(fa, st) : launch_tile_embed<1, 3, false>(fa, st);
+                }
+                if (fe != cudaSuccess) return cuda_fail(fe, "svs_embed_frames launch (tile)");
+            }
             g_launches.fetch_add(1);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (packed)");

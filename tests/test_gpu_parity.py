@@ -85,10 +85,11 @@ def test_dropin_edge_semantics():
 
 
 # ------------------------------------------------------------------ batched API vs the C oracle
-@pytest.fixture(params=["packed", "scalar"])
+@pytest.fixture(params=["tile", "lockstep", "scalar"])
 def kernel_family(request):
-    """Run a test once through the packed-FP32 kernels and once through the scalar kernels."""
-    prev = svs_b200.lib().svs_debug_force_scalar(1 if request.param == "scalar" else 0)
+    """Run a test through each kernel family: packed tile (default), packed lockstep, scalar."""
+    mode = {"scalar": 1, "lockstep": 2, "tile": 3}[request.param]
+    prev = svs_b200.lib().svs_debug_force_scalar(mode)
     yield request.param
     svs_b200.lib().svs_debug_force_scalar(prev)
 
