@@ -131,7 +131,7 @@ int svs_embed_frames_host(svs_ctx* ctx, const uint8_t* h_frames, int channels, i
 /* Number of kernels this library has launched in the calling process (for bench accounting). */
 int64_t svs_kernel_launch_count(void);
 
-/* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 "tile" kernels
+/* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 lockstep kernels
  * whenever they apply, scalar kernels otherwise), 1 = scalar one-block-per-thread kernels only,
  * 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh); negative
  * only queries.  Returns the previous setting.  All families produce identical results; the

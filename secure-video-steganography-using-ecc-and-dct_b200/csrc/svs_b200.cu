@@ -481,7 +481,7 @@ unsigned fast_grid(long long total_groups)
     return (unsigned)(want < cap ? want : cap);
 }
 
-// Kernel family: 0 = automatic (packed "tile" kernels when applicable), 1 = scalar only,
+// Kernel family: 0 = automatic (packed lockstep kernels when applicable), 1 = scalar only,
 // 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh).
 int g_family = 0;
 
@@ -597,7 +597,7 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
         fa.bits_frame_stride = bits_frame_stride;
         const bool full = a.g.n == SVS_MAX_AC;
         cudaError_t fe;
-        if (family() == 2) {
+        if (family() != 3) {
             const unsigned fgrid = fast_grid(fa.g.total_groups);
             if (channels == 3) {
                 if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
@@ -688,7 +688,7 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fa.stego_row_stride = stego_row_stride;
             fa.bits_embedded = d_bits_embedded_out;
             const bool nfull = a.g.n == SVS_MAX_AC;
-            if (family() == 2) {
+            if (family() != 3) {
                 const unsigned fgrid = fast_grid(fa.g.total_groups);
 #define SVS_LAUNCH_EMBED(CH, OC)                                                                         \
     do {                                                                                                 \

@@ -142,27 +142,27 @@ __device__ __forceinline__ uint32_t magic_byte(uint32_t v, uint32_t magic_hi)
     return __byte_perm(v, magic_hi, 0x7540 | SEL);
 }
 
-// Row of one block -> its 8 gray bytes in two words (BGR: cv2 BGR2GRAY through two dp2a).
+// Row words of one block (in registers) -> its 8 gray bytes in two words.  BGR: cv2 BGR2GRAY,
+// 2*(3735 B + 19235 G + 9798 R + 16384) < 2^24 through two dp2a per pixel with the 16-bit weights
+// placed according to where the pixel's three bytes sit in the row's words (no byte shuffles);
+// the gray value is bits 16..23 of the sum.
 template <int CH>
-__device__ __forceinline__ void load_row_gray(const uint8_t* __restrict__ row, uint32_t& lo, uint32_t& hi)
+__device__ __forceinline__ void row_to_gray(const uint2* w, uint32_t& lo, uint32_t& hi)
 {
     if (CH == 1) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(row));
-        lo = v.x;
-        hi = v.y;
+        lo = w[0].x;
+        hi = w[0].y;
     } else {
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(row));
-        const uint2 b = __ldg(reinterpret_cast<const uint2*>(row) + 1);
-        const uint2 c = __ldg(reinterpret_cast<const uint2*>(row) + 2);
-        const uint32_t w[7] = {a.x, a.y, b.x, b.y, c.x, c.y, 0u};
+        constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
+        const uint32_t v[6] = {w[0].x, w[0].y, w[1].x, w[1].y, w[2].x, w[2].y};
         uint32_t s[8];
 #pragma unroll
         for (int px = 0; px < 8; ++px) {
             const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
-            const uint32_t sel = (uint32_t)(off | ((off + 1) << 4) | ((off + 2) << 8) | ((off + 3) << 12));
-            const uint32_t bgr = off == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sel);
-            // 2*(3735 B + 19235 G + 9798 R + 16384) < 2^24: gray = bits 16..23 of the sum
-            s[px] = __dp2a_hi(19596u, bgr, __dp2a_lo((38470u << 16) | 7470u, bgr, 32768u));
+            if (off == 0)      s[px] = __dp2a_hi(WR, v[wi], __dp2a_lo((WG << 16) | WB, v[wi], RND));
+            else if (off == 1) s[px] = __dp2a_hi((WR << 16) | WG, v[wi], __dp2a_lo(WB << 16, v[wi], RND));
+            else if (off == 2) s[px] = __dp2a_lo(WR, v[wi + 1], __dp2a_hi((WG << 16) | WB, v[wi], RND));
+            else               s[px] = __dp2a_lo((WR << 16) | WG, v[wi + 1], __dp2a_hi(WB << 16, v[wi], RND));
         }
         lo = __byte_perm(__byte_perm(s[0], s[1], 0x0062), __byte_perm(s[2], s[3], 0x0062), 0x5410);
         hi = __byte_perm(__byte_perm(s[4], s[5], 0x0062), __byte_perm(s[6], s[7], 0x0062), 0x5410);
@@ -309,42 +309,36 @@ __device__ __forceinline__ Lane locate(const FastGeom& G, long long g, int lane)
     return L;
 }
 
+// Raw row words of one block of the lane (8 rows x P 8-byte words) -> registers.
 template <int CH>
-__device__ __forceinline__ void prefetch_group(const FastGeom& G, long long g, int lane)
+__device__ __forceinline__ void load_block_raw(const FastGeom& G, int f, int by, int bx, uint2* raw)
 {
-    if (g >= G.total_groups) return;
-    const Lane L = locate(G, g, lane);
-    const uint8_t* frame = G.frames + L.f * G.frame_stride;
-    const uint8_t* pA = frame + (long long)(L.byA * 8) * G.row_stride + L.bxA * (8 * CH);
-    const uint8_t* pB = frame + (long long)(L.byB * 8) * G.row_stride + L.bxB * (8 * CH);
+    constexpr int P = CH == 3 ? 3 : 1;
+    const uint8_t* p = G.frames + f * G.frame_stride + (long long)(by * 8) * G.row_stride + bx * (8 * CH);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pA));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pB));
-        step(pA, G.row_stride);
-        step(pB, G.row_stride);
+#pragma unroll
+        for (int j = 0; j < P; ++j) raw[r * P + j] = __ldg(reinterpret_cast<const uint2*>(p) + j);
+        step(p, G.row_stride);
     }
 }
-#ifdef SVS_L2_PREFETCH          // measured: no gain on B200 (2.24 ms vs 2.20 ms per 600 frames), off by default
-#define SVS_PREFETCH(CH, G, g, lane) prefetch_group<CH>(G, g, lane)
-#else
-#define SVS_PREFETCH(CH, G, g, lane) ((void)0)
-#endif
 
-// Loads both blocks of this lane as packed gray bytes (g[2r], g[2r+1] = row r).
 template <int CH>
-__device__ __forceinline__ void load_blocks_gray(const FastGeom& G, const Lane& L, uint32_t (&gA)[16], uint32_t (&gB)[16])
+__device__ __forceinline__ void raw_to_gray(const uint2* raw, uint32_t (&g)[16])
 {
-    const uint8_t* frame = G.frames + L.f * G.frame_stride;
-    const uint8_t* pA = frame + (long long)(L.byA * 8) * G.row_stride + L.bxA * (8 * CH);
-    const uint8_t* pB = frame + (long long)(L.byB * 8) * G.row_stride + L.bxB * (8 * CH);
+    constexpr int P = CH == 3 ? 3 : 1;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        load_row_gray<CH>(pA, gA[2 * r], gA[2 * r + 1]);
-        load_row_gray<CH>(pB, gB[2 * r], gB[2 * r + 1]);
-        step(pA, G.row_stride);
-        step(pB, G.row_stride);
-    }
+    for (int r = 0; r < 8; ++r) row_to_gray<CH>(raw + r * P, g[2 * r], g[2 * r + 1]);
+}
+
+// The lane's blocks for group g; warps past the end of the work redo the last group with their
+// stores masked so that every warp of the CTA executes the same instruction stream.
+__device__ __forceinline__ Lane locate_or_idle(const FastGeom& G, long long g, int lane, bool& live)
+{
+    live = g < G.total_groups;
+    Lane L = locate(G, live ? g : G.total_groups - 1, lane);
+    if (!live) { L.okA = false; L.okB = false; }
+    return L;
 }
 
 // Column c of both blocks -> 8 packed floats, then the axis-0 transform of that column; written
@@ -377,20 +371,26 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     const uint32_t emask = a.q.emask, ebit = a.q.ebit;
     const int erot = a.q.erot;
 
-    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += (long long)gridDim.x * kFastWarps) {
+    // The raw input words of a group are loaded into registers while the PREVIOUS group is
+    // being written out (its coefficient registers die row by row), so that the HBM latency is
+    // not paid by twelve warps at once at the top of every group.
+    constexpr int P = CH == 3 ? 3 : 1;
+    uint2 rawA[8 * P], rawB[8 * P];
+    const long long gstep = (long long)gridDim.x * kFastWarps;
+    bool live;
+    Lane L = locate_or_idle(G, (long long)blockIdx.x * kFastWarps + warp, lane, live);
+    load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
+    load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
+
+    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
         SVS_LOCKSTEP();                        // keep the warps of the CTA in one instruction-cache window
-        long long g = g0 + warp;
-        const bool live = g < G.total_groups;          // idle warps redo the last group, stores masked
-        if (!live) g = G.total_groups - 1;
-        Lane L = locate(G, g, lane);
-        if (!live) { L.okA = false; L.okB = false; }
-        SVS_PREFETCH(CH, G, g + (long long)gridDim.x * kFastWarps, lane);
         if (live && L.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[L.f] = a.cap;
 
         P2 x[64];
         {
             uint32_t gA[16], gB[16];
-            load_blocks_gray<CH>(G, L, gA, gB);
+            raw_to_gray<CH>(rawA, gA);
+            raw_to_gray<CH>(rawB, gB);
             column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
             column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
             column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
@@ -458,6 +458,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
         uint8_t* out = a.stego + L.f * a.stego_frame_stride;
         uint8_t* dstA = out + (long long)(L.byA * 8) * a.stego_row_stride + L.bxA * (8 * OUT_CH);
         uint8_t* dstB = out + (long long)(L.byB * 8) * a.stego_row_stride + L.bxB * (8 * OUT_CH);
+        const bool okA = L.okA, okB = L.okB;
+        L = locate_or_idle(G, g0 + gstep + warp, lane, live);          // the next group of this warp
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             svs::dct8_inv<1>(ops, x + 8 * r);
@@ -471,11 +473,14 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
             }
             const uint32_t a0 = pack4(ba[0], ba[1], ba[2], ba[3]), a1 = pack4(ba[4], ba[5], ba[6], ba[7]);
             const uint32_t b0 = pack4(bb[0], bb[1], bb[2], bb[3]), b1 = pack4(bb[4], bb[5], bb[6], bb[7]);
-            if (L.okA) store_row<OUT_CH>(dstA, a0, a1);
-            if (L.okB) store_row<OUT_CH>(dstB, b0, b1);
+            if (okA) store_row<OUT_CH>(dstA, a0, a1);
+            if (okB) store_row<OUT_CH>(dstB, b0, b1);
             step(dstA, a.stego_row_stride);
             step(dstB, a.stego_row_stride);
             if (r == 3) SVS_LOCKSTEP3();
+            // rows 0..r of x are dead now: their registers take the next group's input
+            if (r == 3) load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
+            if (r == 6) load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
         }
     }
 }
@@ -496,27 +501,33 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
     const uint32_t xmask = a.q.xmask;
     const int xk = a.q.xk;
 
-    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += (long long)gridDim.x * kFastWarps) {
+    constexpr int P = CH == 3 ? 3 : 1;
+    uint2 rawA[8 * P], rawB[8 * P];
+    const long long gstep = (long long)gridDim.x * kFastWarps;
+    bool live;
+    Lane L = locate_or_idle(G, (long long)blockIdx.x * kFastWarps + warp, lane, live);
+    load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
+    load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
+
+    for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
         SVS_LOCKSTEP();
-        long long g = g0 + warp;
-        const bool live = g < G.total_groups;
-        if (!live) g = G.total_groups - 1;
-        Lane L = locate(G, g, lane);
-        if (!live) { L.okA = false; L.okB = false; }
-        SVS_PREFETCH(CH, G, g + (long long)gridDim.x * kFastWarps, lane);
 #pragma unroll
         for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
 
         P2 x[64];
         {
             uint32_t gA[16], gB[16];
-            load_blocks_gray<CH>(G, L, gA, gB);
+            raw_to_gray<CH>(rawA, gA);
+            raw_to_gray<CH>(rawB, gB);
             column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
             column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
             column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
             column_fwd<6>(ops, gA, gB, G.magic_hi, x); column_fwd<7>(ops, gA, gB, G.magic_hi, x);
         }
         SVS_LOCKSTEP2();
+        const Lane C = L;                                      // current group (for the output)
+        const bool clive = live;
+        L = locate_or_idle(G, g0 + gstep + warp, lane, live);  // next group: loaded during the quantiser
 
         uint32_t hiA = 0, loA = 0, hiB = 0, loB = 0;            // bit i at (hi:lo) bit 63-i
 #pragma unroll
@@ -552,9 +563,11 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
                 else if (u == 4) { hiA |= rowA >> 7; loA |= rowA << 25; hiB |= rowB >> 7; loB |= rowB << 25; }
                 else             { loA |= rowA << (57 - 8 * u); loB |= rowB << (57 - 8 * u); }
             }
+            if (u == 3) load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
+            if (u == 6) load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
         }
-        if (!L.okA) { hiA = 0; loA = 0; }
-        if (!L.okB) { hiB = 0; loB = 0; }
+        if (!C.okA) { hiA = 0; loA = 0; }
+        if (!C.okB) { hiB = 0; loB = 0; }
         __syncwarp();
         {
             // place the two n-bit strings at bit offsets lane*n and (32+lane)*n of the warp's run
@@ -571,9 +584,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
             if (p2) atomicOr(p + w0 + 2, p2);
         }
         __syncwarp();
-        const int nblk = live ? min(64, G.bpf - L.base) : 0;
+        const int nblk = clive ? min(64, G.bpf - C.base) : 0;
         const int nwords = (nblk * n + 31) >> 5;
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + L.f * a.bits_frame_stride + (long long)(L.base >> 5) * (4 * n));
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + C.f * a.bits_frame_stride + (long long)(C.base >> 5) * (4 * n));
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (lane + 32 * j < nwords) o32[lane + 32 * j] = bswap(pack[warp][lane + 32 * j]);
