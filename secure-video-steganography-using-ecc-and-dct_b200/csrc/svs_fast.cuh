@@ -101,7 +101,10 @@ constexpr int kFastWarps = kFastThreads / 32;
 #ifndef SVS_SYNC_LEVEL
 #define SVS_SYNC_LEVEL 1
 #endif
-#define SVS_LOCKSTEP() do { if (SVS_SYNC_LEVEL >= 1) __syncthreads(); } while (0)
+#ifndef SVS_SYNC_EVERY
+#define SVS_SYNC_EVERY 1
+#endif
+#define SVS_LOCKSTEP() do { if (SVS_SYNC_LEVEL >= 1 && (SVS_SYNC_EVERY == 1 || (iter++ % SVS_SYNC_EVERY) == 0)) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP2() do { if (SVS_SYNC_LEVEL >= 2) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP3() do { if (SVS_SYNC_LEVEL >= 3) __syncthreads(); } while (0)
 constexpr uint32_t kZone = 4;                     // flagged when fraction bits < kZone (shift = 2 ulp)
@@ -323,6 +326,22 @@ __device__ __forceinline__ void load_block_raw(const FastGeom& G, int f, int by,
     }
 }
 
+// Pulls the lane's rows of a (future) group into L2; no registers are held.
+template <int CH>
+__device__ __forceinline__ void prefetch_l2(const FastGeom& G, const Lane& L)
+{
+    const uint8_t* frame = G.frames + L.f * G.frame_stride;
+    const uint8_t* pA = frame + (long long)(L.byA * 8) * G.row_stride + L.bxA * (8 * CH);
+    const uint8_t* pB = frame + (long long)(L.byB * 8) * G.row_stride + L.bxB * (8 * CH);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pA));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pB));
+        step(pA, G.row_stride);
+        step(pB, G.row_stride);
+    }
+}
+
 template <int CH>
 __device__ __forceinline__ void raw_to_gray(const uint2* raw, uint32_t (&g)[16])
 {
@@ -382,9 +401,18 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
     load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
 
+    unsigned iter = 0;
+    (void)iter;
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
         SVS_LOCKSTEP();                        // keep the warps of the CTA in one instruction-cache window
         if (live && L.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[L.f] = a.cap;
+#ifdef SVS_L2_PREFETCH
+        {
+            bool nl;
+            const Lane N = locate_or_idle(G, g0 + gstep + warp, lane, nl);
+            prefetch_l2<CH>(G, N);
+        }
+#endif
 
         P2 x[64];
         {
@@ -509,8 +537,10 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
     load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
     load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
 
+    unsigned iter = 0;
+    (void)iter;
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
-        SVS_LOCKSTEP();
+        if ((iter++ & 3u) == 0) SVS_LOCKSTEP();          // small code: a loose lockstep is enough here
 #pragma unroll
         for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
 
