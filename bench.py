@@ -237,7 +237,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the kernels are persistent and fill every SM: leave a few SMs to the all-gather so that it
+        # really overlaps the next batch, and tell NCCL not to ask for more CTAs than that
+        reserved = int(os.environ.get("SVS_RESERVED_SMS", "8"))
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, reserved)))
         dist.init_process_group("nccl", device_id=dev)
+        svs_b200.lib().svs_set_reserved_sms(reserved)
     args.warmup = max(args.warmup, 3)
 
     F = FRAMES_PER_GPU
@@ -250,7 +255,12 @@ def main():
     stego = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
     pitch = svs_b200.bits_row_bytes(H, W, NUM_AC)
     bits = torch.empty((F, pitch), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world * F, pitch), dtype=torch.uint8, device=dev) if world > 1 else None
+    nchunks = int(os.environ.get("SVS_GATHER_CHUNKS", "2"))      # 0: plain all-gather on the compute stream
+    overlap = sharding.OverlappedExtractGather(F, pitch, dev, chunks=nchunks) if world > 1 and nchunks > 0 else None
+    if overlap is not None:
+        bits = overlap.local
+    gathered = overlap.gathered if overlap is not None else (
+        torch.empty((world * F, pitch), dtype=torch.uint8, device=dev) if world > 1 else None)
     L = svs_b200.lib()
     stream = torch.cuda.current_stream()
 
@@ -264,11 +274,14 @@ def main():
         svs_b200.embed_frames(frames, payload, total_bits, DELTA, NUM_AC, out=stego)
         if timed:
             e1.record(stream)
-        svs_b200.extract_frames(stego, DELTA, NUM_AC, out=bits)
+        if overlap is not None:   # chunked extract, each chunk all-gathered on a side stream (overlaps what follows)
+            overlap.run(stego, DELTA, NUM_AC)
+        else:
+            svs_b200.extract_frames(stego, DELTA, NUM_AC, out=bits)
+            if world > 1:
+                sharding.all_gather_bits(bits, out=gathered)
         if timed:
             e2.record(stream)
-        if world > 1:
-            sharding.all_gather_bits(bits, out=gathered)
         if timed:
             e3.record(stream)
             marks.append((e0, e1, e2, e3))
@@ -292,6 +305,8 @@ def main():
     start.record(stream)
     for _ in range(args.steps):
         step(True)
+    if overlap is not None:
+        overlap.wait()              # every gather has landed before the clock stops
     stop.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -340,7 +355,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "frames_per_gpu": F, "height": H, "width": W, "num_ac": NUM_AC,
                    "delta": DELTA, "step": "embed (BGR->gray stego) + extract (gray stego->packed bits)"
-                                           + (" + NCCL all-gather of bits" if world > 1 else ""),
+                                           + (" + NCCL all-gather of bits (chunked, overlapped on a side stream)" if world > 1 else ""),
                    "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % ((eb + xb) / 1e9),
                    "parallelism": "frame-sharded x%d" % world},
         "mpixel_per_s": value * H * W / 1e6,
@@ -351,7 +366,9 @@ def main():
                              "unit": "GB/s", "frac": ach_x / peak, "algorithmic_bytes_per_launch": xb,
                              "launch_ms": extract_ms},
         "roofline_round_trip": {"achieved": ach_rt, "peak": peak, "unit": "GB/s", "frac": ach_rt / peak},
-        "allgather_ms": gather_ms if world > 1 else 0.0,
+        "allgather": None if world == 1 else (
+            "overlapped: %d chunks on a side stream, %s SMs left to NCCL, all complete inside the timed region"
+            % (len(overlap.bounds), os.environ.get("SVS_RESERVED_SMS", "8")) if overlap is not None else "sequential on the compute stream"),
         "gpu_launches": launches, "clocks": clocks, "parity_check": ok,
         "e2e": e2e,
     }

@@ -73,6 +73,23 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
                        void* stream);
 
 /*
+ * svs_extract_frames fused with the all-gather of a frame-sharded job: besides d_bits_out the
+ * kernel stores every row to n_peers (<= 15) further buffers - normally the other ranks' gathered
+ * buffers, peer-mapped over NVLink (CUDA IPC / symmetric memory), each pointer already offset to
+ * where THIS rank's frames belong.  Plain stores from the extract kernel: no separate collective,
+ * no SMs set aside for one.  The rows are complete on a peer once this kernel has finished and
+ * the ranks have synchronised (e.g. a symmetric-memory barrier).  Only the packed kernels do this
+ * (16-byte friendly input, bits_frame_stride from svs_bits_row_bytes, delta >= 1/16); otherwise
+ * SVS_ERR_ALIGNMENT is returned and the caller gathers with NCCL instead.
+ */
+int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_frames,
+                               int height, int width, int64_t frame_stride, int64_t row_stride,
+                               double delta, int num_ac,
+                               uint8_t* d_bits_out, int64_t bits_frame_stride,
+                               uint8_t* const* peer_bits_out, int n_peers,
+                               void* stream);
+
+/*
  * mode == 'embed' for a batch (config_and_setup.py:129-158,166-172).
  * Payload bit i of the batch is bit (payload_bit_offset + i) of d_payload (MSB-first);
  * payload_total_bits bits are available.  d_payload must be 4-byte aligned.
@@ -130,6 +147,12 @@ int svs_embed_frames_host(svs_ctx* ctx, const uint8_t* h_frames, int channels, i
 
 /* Number of kernels this library has launched in the calling process (for bench accounting). */
 int64_t svs_kernel_launch_count(void);
+
+/* The packed kernels are persistent and by default occupy every SM (one CTA per SM with the
+ * whole register file).  A caller that runs a collective (NCCL all-gather of the extracted bits)
+ * concurrently on another stream leaves `n` SMs free for it; n < 0 only queries.  Returns the
+ * previous value.  Process-wide. */
+int svs_set_reserved_sms(int n);
 
 /* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 lockstep kernels
  * whenever they apply, scalar kernels otherwise), 1 = scalar one-block-per-thread kernels only,

@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 4) extract_kernel(const ExtractArgs 
 // ------------------------------------------------------------------------------------------
 thread_local char g_err[256] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_reserved_sms{0};
 
 int fail(int code, const char* fmt, ...)
 {
@@ -477,7 +478,9 @@ unsigned fast_grid(long long total_groups)
         sms[dev] = v;
     }
     const long long want = (total_groups + fast::kFastWarps - 1) / fast::kFastWarps;
-    const long long cap = (long long)sms[dev] * fast::kFastCtasPerSm;
+    int usable = sms[dev] - g_reserved_sms.load();
+    if (usable < 1) usable = 1;
+    const long long cap = (long long)usable * fast::kFastCtasPerSm;
     return (unsigned)(want < cap ? want : cap);
 }
 
@@ -545,6 +548,13 @@ const char* svs_last_error_string(void) { return g_err; }
 
 int64_t svs_kernel_launch_count(void) { return g_launches.load(); }
 
+int svs_set_reserved_sms(int n)
+{
+    const int prev = g_reserved_sms.load();
+    if (n >= 0) g_reserved_sms.store(n);
+    return prev;
+}
+
 int svs_debug_force_scalar(int on)
 {
     const int prev = g_family;
@@ -566,10 +576,11 @@ int64_t svs_bits_row_bytes(int height, int width, int num_ac)
     return (words * 4 + 15) / 16 * 16;
 }
 
-int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
-                       int height, int width, int64_t frame_stride, int64_t row_stride,
-                       double delta, int num_ac,
-                       uint8_t* d_bits_out, int64_t bits_frame_stride, void* stream)
+static int extract_impl(const uint8_t* d_frames, int channels, int64_t n_frames,
+                        int height, int width, int64_t frame_stride, int64_t row_stride,
+                        double delta, int num_ac,
+                        uint8_t* d_bits_out, int64_t bits_frame_stride,
+                        uint8_t* const* peers, int n_peers, void* stream)
 {
     g_err[0] = 0;
     if (int rc = check_geometry(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta)) return rc;
@@ -595,6 +606,8 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
         fa.q = fq;
         fa.bits = d_bits_out;
         fa.bits_frame_stride = bits_frame_stride;
+        fa.n_peers = family() == 3 ? 0 : n_peers;
+        for (int e = 0; e < fa.n_peers; ++e) fa.peers[e] = peers[e];
         const bool full = a.g.n == SVS_MAX_AC;
         cudaError_t fe;
         if (family() != 3) {
@@ -613,12 +626,40 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fe = full ? launch_tile_extract<1, true>(fa, st) : launch_tile_extract<1, false>(fa, st);
         }
         if (fe != cudaSuccess) return cuda_fail(fe, "svs_extract_frames launch (packed)");
+    } else if (n_peers > 0) {
+        return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed kernels (aligned input, padded bit rows, delta >= 1/16)");
     } else if (channels == 3) { if (al) launch_extract<3, true>(a, words, (unsigned)grid, st); else launch_extract<3, false>(a, words, (unsigned)grid, st); }
     else                      { if (al) launch_extract<1, true>(a, words, (unsigned)grid, st); else launch_extract<1, false>(a, words, (unsigned)grid, st); }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "svs_extract_frames launch");
     return SVS_OK;
+}
+
+int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
+                       int height, int width, int64_t frame_stride, int64_t row_stride,
+                       double delta, int num_ac,
+                       uint8_t* d_bits_out, int64_t bits_frame_stride, void* stream)
+{
+    return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
+                        d_bits_out, bits_frame_stride, nullptr, 0, stream);
+}
+
+int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_frames,
+                               int height, int width, int64_t frame_stride, int64_t row_stride,
+                               double delta, int num_ac,
+                               uint8_t* d_bits_out, int64_t bits_frame_stride,
+                               uint8_t* const* peer_bits_out, int n_peers, void* stream)
+{
+    g_err[0] = 0;
+    if (n_peers < 0 || n_peers > fast::kMaxPeers) return fail(SVS_ERR_SHAPE, "n_peers must be 0..%d", fast::kMaxPeers);
+    if (n_peers > 0 && peer_bits_out == nullptr) return fail(SVS_ERR_POINTER, "peer_bits_out is NULL");
+    for (int e = 0; e < n_peers; ++e)
+        if (peer_bits_out[e] == nullptr || !aligned_to(peer_bits_out[e], 0, 0, 4))
+            return fail(SVS_ERR_ALIGNMENT, "peer buffer %d is NULL or not 4-byte aligned", e);
+    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed lockstep kernels");
+    return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
+                        d_bits_out, bits_frame_stride, peer_bits_out, n_peers, stream);
 }
 
 int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,

@@ -129,11 +129,16 @@ struct FastEmbedArgs {
     int64_t* bits_embedded;
 };
 
+constexpr int kMaxPeers = 15;
+
 struct FastExtractArgs {
     FastGeom g;
     FastQuant q;
     uint8_t* bits;
     long long bits_frame_stride;
+    // fused all-gather: the same rows are also stored to these (peer-mapped, NVLink) buffers
+    uint8_t* peers[kMaxPeers];
+    int n_peers;
 };
 
 __device__ __forceinline__ uint32_t bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
@@ -617,9 +622,21 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
         const int nblk = clive ? min(64, G.bpf - C.base) : 0;
         const int nwords = (nblk * n + 31) >> 5;
         uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + C.f * a.bits_frame_stride + (long long)(C.base >> 5) * (4 * n));
+        const long long row_off = C.f * a.bits_frame_stride + (long long)(C.base >> 5) * (4 * n);
+        uint32_t wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < nwords) o32[lane + 32 * j] = bswap(pack[warp][lane + 32 * j]);
+        for (int j = 0; j < 4; ++j) {
+            wv[j] = bswap(pack[warp][lane + 32 * j]);
+            if (lane + 32 * j < nwords) o32[lane + 32 * j] = wv[j];
+        }
+        // fused all-gather: the same words go straight into every peer's gathered buffer over
+        // NVLink (plain stores to peer-mapped memory; no separate collective, no SMs set aside)
+        for (int e = 0; e < a.n_peers; ++e) {
+            uint32_t* p32 = reinterpret_cast<uint32_t*>(a.peers[e] + row_off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane + 32 * j < nwords) p32[lane + 32 * j] = wv[j];
+        }
         __syncwarp();
     }
 }
