@@ -236,11 +236,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # multi-GPU exchange of the extracted bits: "fused" = the extract kernel stores its rows straight
+    # into every rank's gathered buffer over NVLink (symmetric memory; multicast when available),
+    # "nccl" = chunked extract + ncclAllGather overlapped on a side stream, "nccl-seq" = plain all-gather
+    gather_mode = os.environ.get("SVS_GATHER", "fused") if world > 1 else "none"
     if world > 1:
-        # the kernels are persistent and fill every SM: leave a few SMs to the all-gather so that it
-        # really overlaps the next batch, and tell NCCL not to ask for more CTAs than that
-        reserved = int(os.environ.get("SVS_RESERVED_SMS", "8"))
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, reserved)))
+        reserved = int(os.environ.get("SVS_RESERVED_SMS", "8")) if gather_mode == "nccl" else 0
+        if gather_mode == "nccl":
+            # the kernels are persistent and fill every SM: leave a few SMs to the all-gather so that
+            # it really overlaps, and tell NCCL not to ask for more CTAs than that
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, reserved)))
         dist.init_process_group("nccl", device_id=dev)
         svs_b200.lib().svs_set_reserved_sms(reserved)
     args.warmup = max(args.warmup, 3)
@@ -255,12 +260,20 @@ def main():
     stego = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
     pitch = svs_b200.bits_row_bytes(H, W, NUM_AC)
     bits = torch.empty((F, pitch), dtype=torch.uint8, device=dev)
-    nchunks = int(os.environ.get("SVS_GATHER_CHUNKS", "2"))      # 0: plain all-gather on the compute stream
-    overlap = sharding.OverlappedExtractGather(F, pitch, dev, chunks=nchunks) if world > 1 and nchunks > 0 else None
-    if overlap is not None:
-        bits = overlap.local
-    gathered = overlap.gathered if overlap is not None else (
-        torch.empty((world * F, pitch), dtype=torch.uint8, device=dev) if world > 1 else None)
+    overlap = fused = None
+    gathered = None
+    if gather_mode == "fused":
+        try:
+            fused = sharding.FusedExtractGather(F, pitch, dev, use_multicast=os.environ.get("SVS_MULTICAST", "1") != "0")
+            bits, gathered = fused.local, fused.gathered
+        except Exception as exc:       # no peer mapping on this box: say so and use NCCL (every rank fails alike)
+            sys.stderr.write("rank %d: symmetric memory unavailable (%r); falling back to NCCL all-gather\n" % (rank, exc))
+            gather_mode = "nccl"
+    if gather_mode == "nccl":
+        overlap = sharding.OverlappedExtractGather(F, pitch, dev, chunks=int(os.environ.get("SVS_GATHER_CHUNKS", "2")))
+        bits, gathered = overlap.local, overlap.gathered
+    elif world > 1 and fused is None:
+        gathered = torch.empty((world * F, pitch), dtype=torch.uint8, device=dev)
     L = svs_b200.lib()
     stream = torch.cuda.current_stream()
 
@@ -274,7 +287,9 @@ def main():
         svs_b200.embed_frames(frames, payload, total_bits, DELTA, NUM_AC, out=stego)
         if timed:
             e1.record(stream)
-        if overlap is not None:   # chunked extract, each chunk all-gathered on a side stream (overlaps what follows)
+        if fused is not None:     # one kernel: extract + stores into every rank's gathered buffer, then a barrier
+            fused.run(stego, DELTA, NUM_AC)
+        elif overlap is not None:  # chunked extract, each chunk all-gathered on a side stream (overlaps what follows)
             overlap.run(stego, DELTA, NUM_AC)
         else:
             svs_b200.extract_frames(stego, DELTA, NUM_AC, out=bits)
@@ -328,9 +343,30 @@ def main():
 
     # correctness of what was timed: mid-range frames -> the round trip returns the payload
     ok = bool(torch.equal(bits[:, :nbytes].reshape(-1), payload))
+    parity_detail = {"own_rows": ok}
     if world > 1:
         mine = gathered[rank * F:(rank + 1) * F, :nbytes].reshape(-1)
-        ok = ok and bool(torch.equal(mine, payload))
+        parity_detail["own_rows_in_gathered"] = bool(torch.equal(mine, payload))
+        # ... and every OTHER rank's rows arrived intact: compare per-rank checksums of the gathered
+        # stream with the checksums the owners computed from their payloads
+        w8 = torch.arange(1, 8192 + 1, device=dev, dtype=torch.int64)
+
+        def checksum(rows):
+            v = rows.reshape(-1).to(torch.int64)
+            pad = (-v.numel()) % w8.numel()
+            v = torch.nn.functional.pad(v, (0, pad)).reshape(-1, w8.numel())
+            return (v * w8).sum()
+
+        own = checksum(payload).reshape(1)
+        sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, own)
+        torch.cuda.synchronize()
+        per_rank = [int(checksum(gathered[r * F:(r + 1) * F, :nbytes])) == int(sums[r]) for r in range(world)]
+        parity_detail["rows_of_rank_ok"] = per_rank
+        ok = ok and parity_detail["own_rows_in_gathered"] and all(per_rank)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
 
     # ---------------- e2e through the host-buffer C ABI (pinned host memory) ----------------
     e2e = None
@@ -355,7 +391,9 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "frames_per_gpu": F, "height": H, "width": W, "num_ac": NUM_AC,
                    "delta": DELTA, "step": "embed (BGR->gray stego) + extract (gray stego->packed bits)"
-                                           + (" + NCCL all-gather of bits (chunked, overlapped on a side stream)" if world > 1 else ""),
+                                           + {"none": "", "fused": " + all-gather of the bits fused into the extract kernel (stores to every rank's buffer over NVLink) + symmetric-memory barrier",
+                                              "nccl": " + NCCL all-gather of bits (chunked, overlapped on a side stream)",
+                                              "nccl-seq": " + NCCL all-gather of bits"}[gather_mode],
                    "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % ((eb + xb) / 1e9),
                    "parallelism": "frame-sharded x%d" % world},
         "mpixel_per_s": value * H * W / 1e6,
@@ -367,9 +405,12 @@ def main():
                              "launch_ms": extract_ms},
         "roofline_round_trip": {"achieved": ach_rt, "peak": peak, "unit": "GB/s", "frac": ach_rt / peak},
         "allgather": None if world == 1 else (
-            "overlapped: %d chunks on a side stream, %s SMs left to NCCL, all complete inside the timed region"
-            % (len(overlap.bounds), os.environ.get("SVS_RESERVED_SMS", "8")) if overlap is not None else "sequential on the compute stream"),
-        "gpu_launches": launches, "clocks": clocks, "parity_check": ok,
+            "fused into extract_kernel: %s over NVLink into symmetric memory, barrier after each launch" % fused.mode
+            if fused is not None else
+            "NCCL, overlapped: %d chunks on a side stream, %s SMs left to NCCL, all complete inside the timed region"
+            % (len(overlap.bounds), os.environ.get("SVS_RESERVED_SMS", "8")) if overlap is not None
+            else "NCCL, sequential on the compute stream"),
+        "gpu_launches": launches, "clocks": clocks, "parity_check": ok, "parity_detail": parity_detail,
         "e2e": e2e,
     }
     if world == 1 and not args.no_cpu:

@@ -90,6 +90,20 @@ int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_
                                void* stream);
 
 /*
+ * The same fused all-gather through ONE NVSwitch multicast (multimem) address: mc_bits_out maps
+ * the gathered buffer of every rank of the job at once (CUDA multicast object / torch symmetric
+ * memory `multicast_ptr`), already offset to where THIS rank's frames belong.  Every packed word
+ * leaves the GPU once (multimem.st) and the switch replicates it to all ranks, this one included:
+ * d_bits_local only has to be a valid local alias of the same rows (used for argument checks;
+ * the packed kernels do not write it separately).  Same restrictions as the scatter variant.
+ */
+int svs_extract_frames_multicast(const uint8_t* d_frames, int channels, int64_t n_frames,
+                                 int height, int width, int64_t frame_stride, int64_t row_stride,
+                                 double delta, int num_ac,
+                                 uint8_t* mc_bits_out, uint8_t* d_bits_local, int64_t bits_frame_stride,
+                                 void* stream);
+
+/*
  * mode == 'embed' for a batch (config_and_setup.py:129-158,166-172).
  * Payload bit i of the batch is bit (payload_bit_offset + i) of d_payload (MSB-first);
  * payload_total_bits bits are available.  d_payload must be 4-byte aligned.
@@ -156,7 +170,8 @@ int svs_set_reserved_sms(int n);
 
 /* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 lockstep kernels
  * whenever they apply, scalar kernels otherwise), 1 = scalar one-block-per-thread kernels only,
- * 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh); negative
+ * 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh), 4 = packed
+ * row kernels (svs_row.cuh, 8 lanes per block pair); negative
  * only queries.  Returns the previous setting.  All families produce identical results; the
  * tests use this to prove it.  Environment variable SVS_KERNEL_FAMILY sets the default. */
 int svs_debug_force_scalar(int on);

@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
-           os.path.join(_PKG, "csrc", "svs_tile.cuh"),
+           os.path.join(_PKG, "csrc", "svs_tile.cuh"), os.path.join(_PKG, "csrc", "svs_row.cuh"),
            os.path.join(_ROOT, "include", "svs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
@@ -71,6 +71,9 @@ _SIGNATURES = {
     "svs_extract_frames_scatter": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
                                               _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64,
                                               _c.POINTER(_c.c_void_p), _c.c_int, _c.c_void_p]),
+    "svs_extract_frames_multicast": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
+                                                _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                                _c.c_int64, _c.c_void_p]),
     "svs_embed_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
                                     _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_double, _c.c_int,
                                     _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p,
@@ -94,7 +97,8 @@ def lib():
             raise RuntimeError(
                 "libsvs_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                 "this package has no CPU fallback." % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+        # SVS_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
+        L = ctypes.CDLL(os.environ.get("SVS_B200_LIB") or LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

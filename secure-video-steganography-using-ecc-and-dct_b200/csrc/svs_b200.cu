@@ -25,6 +25,7 @@
 #include "svs_math.cuh"
 #include "svs_fast.cuh"
 #include "svs_tile.cuh"
+#include "svs_row.cuh"
 
 namespace {
 
@@ -462,6 +463,7 @@ fast::FastGeom make_fast_geometry(const Geometry& g, long long n_frames)
     f.total_groups = n_frames * f.groups_per_frame;
     f.delta32 = g.delta32;
     f.magic_hi = 0x4B000000u;
+    f.bw_magic = (uint32_t)((0x100000000ull + (unsigned long long)g.bw - 1) / (unsigned long long)g.bw);
     return f;
 }
 
@@ -485,7 +487,8 @@ unsigned fast_grid(long long total_groups)
 }
 
 // Kernel family: 0 = automatic (packed lockstep kernels when applicable), 1 = scalar only,
-// 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh).
+// 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh),
+// 4 = packed row kernels (svs_row.cuh: 8 lanes per block pair).
 int g_family = 0;
 
 int family()
@@ -493,9 +496,24 @@ int family()
     static int env = -1;
     if (env < 0) {
         const char* e = getenv("SVS_KERNEL_FAMILY");
-        env = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+        env = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
     }
     return g_family != 0 ? g_family : env;
+}
+
+// row kernels: free-running warps, kRowCtasPerSm CTAs on every usable SM, grid-stride over groups
+unsigned row_grid(long long total_groups)
+{
+    const long long ctas = (long long)fast_grid(1ll << 40) / fast::kFastCtasPerSm * row::kRowCtasPerSm;
+    const long long want = (total_groups + row::kRowWarps - 1) / row::kRowWarps;
+    return (unsigned)(want < ctas ? want : ctas);
+}
+
+// the row kernels pair horizontally adjacent blocks and use 128-bit loads / stores
+bool row_ok(const Geometry& g, const void* frames, long long frame_stride, long long row_stride)
+{
+    return (g.bw % 2) == 0 && g.bw >= 8 && aligned_to(frames, frame_stride, row_stride, 16) &&
+           (unsigned long long)g.bpf * (unsigned long long)g.bw < 0xffffffffull;
 }
 
 unsigned tile_grid(long long total_groups)
@@ -558,7 +576,7 @@ int svs_set_reserved_sms(int n)
 int svs_debug_force_scalar(int on)
 {
     const int prev = g_family;
-    if (on >= 0 && on <= 3) g_family = on;
+    if (on >= 0 && on <= 4) g_family = on;
     return prev;
 }
 
@@ -580,7 +598,7 @@ static int extract_impl(const uint8_t* d_frames, int channels, int64_t n_frames,
                         int height, int width, int64_t frame_stride, int64_t row_stride,
                         double delta, int num_ac,
                         uint8_t* d_bits_out, int64_t bits_frame_stride,
-                        uint8_t* const* peers, int n_peers, void* stream)
+                        uint8_t* const* peers, int n_peers, bool multicast, void* stream)
 {
     g_err[0] = 0;
     if (int rc = check_geometry(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta)) return rc;
@@ -607,10 +625,25 @@ static int extract_impl(const uint8_t* d_frames, int channels, int64_t n_frames,
         fa.bits = d_bits_out;
         fa.bits_frame_stride = bits_frame_stride;
         fa.n_peers = family() == 3 ? 0 : n_peers;
+        fa.multicast = multicast ? 1 : 0;
+        const bool use_row = family() == 4 && row_ok(a.g, d_frames, frame_stride, row_stride);
         for (int e = 0; e < fa.n_peers; ++e) fa.peers[e] = peers[e];
         const bool full = a.g.n == SVS_MAX_AC;
         cudaError_t fe;
-        if (family() != 3) {
+        if (use_row) {
+            const unsigned rgrid = row_grid(fa.g.total_groups);
+            row::RowExtractArgs ra;
+            ra.x = fa;
+            ra.wrap_src = 8 * row_stride - (long long)a.g.bw * 8 * channels;
+            if (channels == 3) {
+                if (full) row::extract_row_kernel<3, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                else row::extract_row_kernel<3, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+            } else {
+                if (full) row::extract_row_kernel<1, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                else row::extract_row_kernel<1, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+            }
+            fe = cudaGetLastError();
+        } else if (family() != 3) {
             const unsigned fgrid = fast_grid(fa.g.total_groups);
             if (channels == 3) {
                 if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
@@ -642,7 +675,7 @@ int svs_extract_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
                        uint8_t* d_bits_out, int64_t bits_frame_stride, void* stream)
 {
     return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
-                        d_bits_out, bits_frame_stride, nullptr, 0, stream);
+                        d_bits_out, bits_frame_stride, nullptr, 0, false, stream);
 }
 
 int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_frames,
@@ -659,7 +692,21 @@ int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_
             return fail(SVS_ERR_ALIGNMENT, "peer buffer %d is NULL or not 4-byte aligned", e);
     if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed lockstep kernels");
     return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
-                        d_bits_out, bits_frame_stride, peer_bits_out, n_peers, stream);
+                        d_bits_out, bits_frame_stride, peer_bits_out, n_peers, false, stream);
+}
+
+int svs_extract_frames_multicast(const uint8_t* d_frames, int channels, int64_t n_frames,
+                                 int height, int width, int64_t frame_stride, int64_t row_stride,
+                                 double delta, int num_ac,
+                                 uint8_t* mc_bits_out, uint8_t* d_bits_local, int64_t bits_frame_stride, void* stream)
+{
+    g_err[0] = 0;
+    if (mc_bits_out == nullptr || !aligned_to(mc_bits_out, 0, 0, 4))
+        return fail(SVS_ERR_ALIGNMENT, "mc_bits_out is NULL or not 4-byte aligned");
+    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_multicast needs the packed lockstep / row kernels");
+    uint8_t* one[1] = {mc_bits_out};
+    return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
+                        d_bits_local, bits_frame_stride, one, 1, true, stream);
 }
 
 int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
@@ -729,7 +776,24 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fa.stego_row_stride = stego_row_stride;
             fa.bits_embedded = d_bits_embedded_out;
             const bool nfull = a.g.n == SVS_MAX_AC;
-            if (family() != 3) {
+            const bool use_row = family() == 4 && row_ok(a.g, d_frames, frame_stride, row_stride) &&
+                                 aligned_to(d_stego_out, stego_frame_stride, stego_row_stride, 16) &&
+                                 a.payload_last_word < 0x7fffffffLL;
+            if (use_row) {
+                const unsigned rgrid = row_grid(fa.g.total_groups);
+                row::RowEmbedArgs ra;
+                ra.e = fa;
+                ra.wrap_src = 8 * row_stride - (long long)a.g.bw * 8 * channels;
+                ra.wrap_dst = 8 * stego_row_stride - (long long)a.g.bw * 8 * stego_channels;
+#define SVS_LAUNCH_ROW_EMBED(CH, OC)                                                                     \
+    do {                                                                                                 \
+        if (nfull) row::embed_row_kernel<CH, OC, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);          \
+        else row::embed_row_kernel<CH, OC, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);               \
+    } while (0)
+                if (channels == 3) { if (stego_channels == 1) SVS_LAUNCH_ROW_EMBED(3, 1); else SVS_LAUNCH_ROW_EMBED(3, 3); }
+                else               { if (stego_channels == 1) SVS_LAUNCH_ROW_EMBED(1, 1); else SVS_LAUNCH_ROW_EMBED(1, 3); }
+#undef SVS_LAUNCH_ROW_EMBED
+            } else if (family() != 3) {
                 const unsigned fgrid = fast_grid(fa.g.total_groups);
 #define SVS_LAUNCH_EMBED(CH, OC)                                                                         \
     do {                                                                                                 \

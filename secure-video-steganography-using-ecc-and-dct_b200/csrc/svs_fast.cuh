@@ -117,6 +117,7 @@ struct FastGeom {
     long long total_groups;                       // n_frames * groups_per_frame
     float delta32;
     uint32_t magic_hi;                            // 0x4B000000, opaque so that it stays in a register
+    uint32_t bw_magic;                            // ceil(2^32 / bw): b / bw == umulhi(b, bw_magic) (svs_row.cuh)
 };
 
 struct FastEmbedArgs {
@@ -136,10 +137,38 @@ struct FastExtractArgs {
     FastQuant q;
     uint8_t* bits;
     long long bits_frame_stride;
-    // fused all-gather: the same rows are also stored to these (peer-mapped, NVLink) buffers
+    // fused all-gather: the same rows are also stored to these (peer-mapped, NVLink) buffers;
+    // multicast != 0: peers[0] is ONE NVSwitch multicast (multimem) address that reaches every
+    // rank including this one, and `bits` is not written separately
     uint8_t* peers[kMaxPeers];
     int n_peers;
+    int multicast;
 };
+
+// Stores the (up to 128) packed words of one 64-block group: to this rank's buffer and to every
+// peer (plain stores into peer-mapped memory), or once to the multicast address.
+__device__ __forceinline__ void store_group_words(const FastExtractArgs& a, long long row_off, int lane, int nwords,
+                                                  const uint32_t (&wv)[4])
+{
+    if (a.multicast) {
+        uint32_t* m32 = reinterpret_cast<uint32_t*>(a.peers[0] + row_off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < nwords)
+                asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(m32 + lane + 32 * j), "r"(wv[j]) : "memory");
+        return;
+    }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + row_off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < nwords) o32[lane + 32 * j] = wv[j];
+    for (int e = 0; e < a.n_peers; ++e) {
+        uint32_t* p32 = reinterpret_cast<uint32_t*>(a.peers[e] + row_off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < nwords) p32[lane + 32 * j] = wv[j];
+    }
+}
 
 __device__ __forceinline__ uint32_t bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
@@ -621,22 +650,11 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
         __syncwarp();
         const int nblk = clive ? min(64, G.bpf - C.base) : 0;
         const int nwords = (nblk * n + 31) >> 5;
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + C.f * a.bits_frame_stride + (long long)(C.base >> 5) * (4 * n));
         const long long row_off = C.f * a.bits_frame_stride + (long long)(C.base >> 5) * (4 * n);
         uint32_t wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            wv[j] = bswap(pack[warp][lane + 32 * j]);
-            if (lane + 32 * j < nwords) o32[lane + 32 * j] = wv[j];
-        }
-        // fused all-gather: the same words go straight into every peer's gathered buffer over
-        // NVLink (plain stores to peer-mapped memory; no separate collective, no SMs set aside)
-        for (int e = 0; e < a.n_peers; ++e) {
-            uint32_t* p32 = reinterpret_cast<uint32_t*>(a.peers[e] + row_off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (lane + 32 * j < nwords) p32[lane + 32 * j] = wv[j];
-        }
+        for (int j = 0; j < 4; ++j) wv[j] = bswap(pack[warp][lane + 32 * j]);
+        store_group_words(a, row_off, lane, nwords, wv);
         __syncwarp();
     }
 }

@@ -14,6 +14,7 @@ There is no CPU path: without the built library and a CUDA device these function
 from __future__ import annotations
 
 import collections
+import ctypes
 import math
 import threading
 
@@ -226,11 +227,17 @@ def embed_frames(frames, payload, total_bits, delta, num_ac=63, *, bit_offset=0,
     return EmbedResult(out, gray, nbits, sse)
 
 
-def extract_frames(frames, delta, num_ac=63, *, out=None, stream=None):
+def extract_frames(frames, delta, num_ac=63, *, out=None, stream=None, peer_ptrs=None, multicast_ptr=None):
     """Extract a batch resident in HBM -> (F, ceil(cap/8)) uint8 view of MSB-first packed bits.
 
     The returned tensor is a view of a buffer whose row pitch is bits_row_bytes(...) so that the
     kernel can use 32-bit stores; pass `out` (F, pitch) to reuse a buffer.
+
+    Fused all-gather of a frame-sharded job (sharding.FusedExtractGather): `peer_ptrs` = device
+    addresses (ints) of the same rows inside every OTHER rank's gathered buffer (peer-mapped over
+    NVLink), or `multicast_ptr` = one NVSwitch multicast address of those rows on ALL ranks; the
+    extract kernel then stores every packed word there as well (svs_extract_frames_scatter /
+    svs_extract_frames_multicast) - no separate collective.
     """
     torch = _torch()
     frames, ch, f, h, w, fs, rs = _batch_geometry(frames)
@@ -240,8 +247,22 @@ def extract_frames(frames, delta, num_ac=63, *, out=None, stream=None):
         return torch.empty((f, 0), dtype=torch.uint8, device=frames.device)
     if out is None:
         out = torch.empty((f, bits_row_bytes(h, w, num_ac)), dtype=torch.uint8, device=frames.device)
+    L = _native.lib()
     with torch.cuda.device(frames.device):
-        rc = _native.lib().svs_extract_frames(frames.data_ptr(), ch, f, h, w, fs, rs, float(delta), int(num_ac),
-                                              out.data_ptr(), int(out.stride(0)), _stream_handle(stream))
-    _native.check(rc, "svs_extract_frames")
+        if multicast_ptr:
+            rc = L.svs_extract_frames_multicast(frames.data_ptr(), ch, f, h, w, fs, rs, float(delta), int(num_ac),
+                                                int(multicast_ptr), out.data_ptr(), int(out.stride(0)),
+                                                _stream_handle(stream))
+            what = "svs_extract_frames_multicast"
+        elif peer_ptrs:
+            arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            rc = L.svs_extract_frames_scatter(frames.data_ptr(), ch, f, h, w, fs, rs, float(delta), int(num_ac),
+                                              out.data_ptr(), int(out.stride(0)), arr, len(peer_ptrs),
+                                              _stream_handle(stream))
+            what = "svs_extract_frames_scatter"
+        else:
+            rc = L.svs_extract_frames(frames.data_ptr(), ch, f, h, w, fs, rs, float(delta), int(num_ac),
+                                      out.data_ptr(), int(out.stride(0)), _stream_handle(stream))
+            what = "svs_extract_frames"
+    _native.check(rc, what)
     return out[:, :nbytes]

@@ -161,3 +161,44 @@ class OverlappedExtractGather:
             if ev is not None:
                 cur.wait_event(ev)
         return self.gathered
+
+
+class FusedExtractGather:
+    """Extract + all-gather as ONE kernel over NVLink peer memory (no NCCL on the data path).
+
+    The gathered buffer (world * F_local rows of `pitch` bytes, frame order) lives in symmetric
+    memory: every rank maps every other rank's copy (CUDA IPC / fabric handles through
+    torch.distributed._symmetric_memory).  The extract kernel stores each packed word of this
+    rank's frames into ITS rows of every rank's copy - through one NVSwitch multicast address
+    when the fabric offers it (each word leaves the GPU once and the switch replicates it), else
+    with plain stores to each peer mapping.  A symmetric-memory barrier on the stream separates
+    producers from consumers: no SMs are set aside for a collective and the transfer overlaps the
+    transform tile by tile.  Result: `gathered` on every rank after `run()` (stream-ordered).
+    """
+
+    def __init__(self, n_local, pitch, device, group=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_local, self.pitch = int(n_local), int(pitch)
+        self.gathered = symm.empty((self.world * self.n_local, self.pitch), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.gathered, self.group)
+        off = self.rank * self.n_local * self.pitch
+        self.local = self.gathered[self.rank * self.n_local:(self.rank + 1) * self.n_local]
+        ptrs = list(self.hdl.buffer_ptrs)
+        self.peer_ptrs = [int(p) + off for r, p in enumerate(ptrs) if r != self.rank]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.multicast_ptr = mc + off if mc else 0
+        self.mode = "multicast" if self.multicast_ptr else "peer stores"
+
+    def run(self, frames_local, delta, num_ac, extract_fn=None):
+        """Enqueue barrier -> extract (+ remote stores) -> barrier on the current stream."""
+        extract_fn = extract_fn or frame_path.extract_frames
+        self.hdl.barrier(channel=0)          # every rank is done reading the previous result
+        if self.multicast_ptr:
+            extract_fn(frames_local, delta, num_ac, out=self.local, multicast_ptr=self.multicast_ptr)
+        else:
+            extract_fn(frames_local, delta, num_ac, out=self.local, peer_ptrs=self.peer_ptrs)
+        self.hdl.barrier(channel=1)          # every rank's rows have landed everywhere
+        return self.gathered

@@ -85,10 +85,11 @@ def test_dropin_edge_semantics():
 
 
 # ------------------------------------------------------------------ batched API vs the C oracle
-@pytest.fixture(params=["tile", "lockstep", "scalar"])
+@pytest.fixture(params=["row", "tile", "lockstep", "scalar"])
 def kernel_family(request):
-    """Run a test through each kernel family: packed tile (default), packed lockstep, scalar."""
-    mode = {"scalar": 1, "lockstep": 2, "tile": 3}[request.param]
+    """Run a test through each kernel family: packed row (8 lanes per block pair), packed tile,
+    packed lockstep, scalar."""
+    mode = {"scalar": 1, "lockstep": 2, "tile": 3, "row": 4}[request.param]
     prev = svs_b200.lib().svs_debug_force_scalar(mode)
     yield request.param
     svs_b200.lib().svs_debug_force_scalar(prev)

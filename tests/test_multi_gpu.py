@@ -44,6 +44,16 @@ def _worker(rank, world, port, outdir):
         plain = sharding.extract_allgather(res.stego, DELTA, N_AC, n_frames_total=F_TOTAL)
         torch.cuda.synchronize()
         assert torch.equal(full, plain)
+        # the fused path: the extract kernel stores into both ranks' symmetric buffers (peer stores, then
+        # the NVSwitch multicast address when the fabric has one); twice, to cover buffer reuse
+        for use_mc in (False, True):
+            fg = sharding.FusedExtractGather(f1 - f0, svs_b200.bits_row_bytes(H, W, N_AC), mine.device, use_multicast=use_mc)
+            for _ in range(2):
+                fg.gathered.zero_()
+                fg.hdl.barrier(channel=2)
+                got = fg.run(res.stego, DELTA, N_AC)[:, :(cap + 7) // 8]
+                torch.cuda.synchronize()
+                assert torch.equal(got, plain), "fused gather (%s) differs" % fg.mode
         np.save(os.path.join(outdir, "bits%d.npy" % rank), full.cpu().numpy())
         np.save(os.path.join(outdir, "stego%d.npy" % rank), res.stego.cpu().numpy())
     finally:
