@@ -239,7 +239,7 @@ def main():
     # multi-GPU exchange of the extracted bits: "fused" = the extract kernel stores its rows straight
     # into every rank's gathered buffer over NVLink (symmetric memory; multicast when available),
     # "nccl" = chunked extract + ncclAllGather overlapped on a side stream, "nccl-seq" = plain all-gather
-    gather_mode = os.environ.get("SVS_GATHER", "fused") if world > 1 else "none"
+    gather_mode = os.environ.get("SVS_GATHER", "push") if world > 1 else "none"
     if world > 1:
         reserved = int(os.environ.get("SVS_RESERVED_SMS", "8")) if gather_mode == "nccl" else 0
         if gather_mode == "nccl":
@@ -269,10 +269,18 @@ def main():
         except Exception as exc:       # no peer mapping on this box: say so and use NCCL (every rank fails alike)
             sys.stderr.write("rank %d: symmetric memory unavailable (%r); falling back to NCCL all-gather\n" % (rank, exc))
             gather_mode = "nccl"
+    if gather_mode == "push":
+        try:
+            overlap = sharding.CopyEngineGather(F, pitch, dev, n_streams=int(os.environ.get("SVS_PUSH_STREAMS", "4")),
+                                                n_buffers=int(os.environ.get("SVS_PUSH_BUFFERS", "2")))
+            bits, gathered = overlap.local, overlap.gathered
+        except Exception as exc:
+            sys.stderr.write("rank %d: symmetric memory unavailable (%r); falling back to NCCL all-gather\n" % (rank, exc))
+            gather_mode = "nccl"
     if gather_mode == "nccl":
         overlap = sharding.OverlappedExtractGather(F, pitch, dev, chunks=int(os.environ.get("SVS_GATHER_CHUNKS", "2")))
         bits, gathered = overlap.local, overlap.gathered
-    elif world > 1 and fused is None:
+    elif world > 1 and fused is None and overlap is None:
         gathered = torch.empty((world * F, pitch), dtype=torch.uint8, device=dev)
     L = svs_b200.lib()
     stream = torch.cuda.current_stream()
@@ -341,6 +349,8 @@ def main():
         ms_total, embed_ms, extract_ms, gather_ms = tmax[:4].tolist()
         launches = int(tsum[4].item())
 
+    if gather_mode == "push":
+        bits, gathered = overlap.local, overlap.gathered       # the buffers of the last step
     # correctness of what was timed: mid-range frames -> the round trip returns the payload
     ok = bool(torch.equal(bits[:, :nbytes].reshape(-1), payload))
     parity_detail = {"own_rows": ok}
@@ -392,6 +402,7 @@ def main():
         "config": {"workload": workload_name(), "frames_per_gpu": F, "height": H, "width": W, "num_ac": NUM_AC,
                    "delta": DELTA, "step": "embed (BGR->gray stego) + extract (gray stego->packed bits)"
                                            + {"none": "", "fused": " + all-gather of the bits fused into the extract kernel (stores to every rank's buffer over NVLink) + symmetric-memory barrier",
+                                              "push": " + all-gather of the bits by DMA into every rank's symmetric buffer (copy engines, overlapped with the next batch) + symmetric-memory barrier",
                                               "nccl": " + NCCL all-gather of bits (chunked, overlapped on a side stream)",
                                               "nccl-seq": " + NCCL all-gather of bits"}[gather_mode],
                    "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % ((eb + xb) / 1e9),
@@ -407,6 +418,7 @@ def main():
         "allgather": None if world == 1 else (
             "fused into extract_kernel: %s over NVLink into symmetric memory, barrier after each launch" % fused.mode
             if fused is not None else
+            "%s; overlaps the next batch, all complete inside the timed region" % overlap.mode if gather_mode == "push" else
             "NCCL, overlapped: %d chunks on a side stream, %s SMs left to NCCL, all complete inside the timed region"
             % (len(overlap.bounds), os.environ.get("SVS_RESERVED_SMS", "8")) if overlap is not None
             else "NCCL, sequential on the compute stream"),
