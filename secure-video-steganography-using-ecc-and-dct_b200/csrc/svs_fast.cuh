@@ -594,10 +594,13 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
         L = locate_or_idle(G, g0 + gstep + warp, lane, live);  // next group: loaded during the quantiser
 
         uint32_t hiA = 0, loA = 0, hiB = 0, loB = 0;            // bit i at (hi:lo) bit 63-i
+        svs::dct8_fwd<1>(ops, x);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
+            // (row u+1 is transformed BEFORE row u is read out, in the same basic block: its FP32
+            // work fills the pipe while the parity read-out keeps the ALU pipe busy)
+            if (u < 7 && (NFULL || 8 * (u + 1) - 1 < n)) svs::dct8_fwd<1>(ops, x + 8 * (u + 1));
             if (NFULL || 8 * u - 1 < n) {
-                svs::dct8_fwd<1>(ops, x + 8 * u);
                 uint32_t worst = 0xffffffffu;
                 uint32_t rowA = 0, rowB = 0;                     // coefficient v of this row at bit 7-v
 #pragma unroll
