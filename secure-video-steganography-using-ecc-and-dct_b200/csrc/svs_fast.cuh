@@ -107,7 +107,10 @@ constexpr int kFastWarps = kFastThreads / 32;
 #define SVS_LOCKSTEP() do { if (SVS_SYNC_LEVEL >= 1 && (SVS_SYNC_EVERY == 1 || (iter++ % SVS_SYNC_EVERY) == 0)) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP2() do { if (SVS_SYNC_LEVEL >= 2) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP3() do { if (SVS_SYNC_LEVEL >= 3) __syncthreads(); } while (0)
-constexpr uint32_t kZone = 4;                     // flagged when fraction bits < kZone (shift = 2 ulp)
+#ifndef SVS_ZONE
+#define SVS_ZONE 4
+#endif
+constexpr uint32_t kZone = SVS_ZONE;                    // flagged when fraction bits < kZone (shift = 2 ulp)
 
 struct FastGeom {
     const uint8_t* frames;
@@ -254,6 +257,45 @@ __device__ __forceinline__ float div_exact(float c, float d, float r)
     float q = __fmul_rn(c, r);
     q = __fmaf_rn(__fmaf_rn(-q, d, c), r, q);
     return __fmaf_rn(__fmaf_rn(-q, d, c), r, q);
+}
+
+// Coefficients (0,4), (4,0) and (4,4) of a block of integer pixels are exact multiples of 1/8
+// (their basis is +-1/8), so c / delta lands EXACTLY on a rounding tie in one block out of
+// 8 delta - far too often for the speculate-and-fix quantiser (a third of all warps would take
+// the out-of-line path in every group, and the slowest warp holds up the lockstep barrier).
+// These three are therefore always quantised with the IEEE division, packed for both blocks:
+// the quotient exactly as div_exact, rint() through the 1.5 * 2^23 constant (round-half-even,
+// the parity is the lowest mantissa bit, two's complement for negative quotients).
+__device__ __forceinline__ bool tie_prone(int flat) { return flat == 4 || flat == 32 || flat == 36; }
+
+struct ExactQ {
+    P2 d, negd, r, magic, negzero;
+    __device__ __forceinline__ P2 rint_quotient_plus_magic(P2 c) const     // 1.5 * 2^23 + rint(c / d)
+    {
+        P2 q = fma2(c, r, negzero);
+        q = fma2(fma2(q, negd, c), r, q);
+        q = fma2(fma2(q, negd, c), r, q);
+        return add2(q, magic);
+    }
+    // q' = q - (q & 1) + bit, returned as float32(q' * d)    (config_and_setup.py:148-156)
+    __device__ __forceinline__ P2 embed(P2 c, uint32_t bitA, uint32_t bitB) const
+    {
+        const P2 m = rint_quotient_plus_magic(c);
+        uint32_t ma, mb;
+        unpk(m, ma, mb);
+        const P2 adj = pk(__int2float_rn((int)bitA - (int)(ma & 1u)), __int2float_rn((int)bitB - (int)(mb & 1u)));
+        return fma2(add2(sub2(m, magic), adj), d, negzero);
+    }
+};
+__device__ __forceinline__ ExactQ make_exact_q(float d32, float r32, float negzero)
+{
+    ExactQ e;
+    e.d = pk(d32, d32);
+    e.negd = pk(-d32, -d32);
+    e.r = pk(r32, r32);
+    e.magic = pk(12582912.0f, 12582912.0f);
+    e.negzero = pk(negzero, negzero);
+    return e;
 }
 
 // Rare path, deliberately out of line and looped so that it costs almost no instruction-cache
@@ -423,6 +465,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     const P2 r2 = pk(a.q.r2, a.q.r2), ke = pk(a.q.ke, a.q.ke), d2 = pk(a.q.d2, a.q.d2), k0 = pk(a.q.k0, a.q.k0);
     const uint32_t emask = a.q.emask, ebit = a.q.ebit;
     const int erot = a.q.erot;
+    const ExactQ exq = make_exact_q(G.delta32, a.q.r, a.q.negzero);
 
     // The raw input words of a group are loaded into registers while the PREVIOUS group is
     // being written out (its coefficient registers die row by row), so that the HBM latency is
@@ -487,7 +530,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
                 for (int v = 0; v < 8; ++v) {
                     const int i = 8 * u + v - 1;                  // payload bit / coefficient number
                     nx[v] = x[8 * u + v];
-                    if (i >= 0 && (NFULL || i < n)) {
+                    if (i >= 0 && (NFULL || i < n) && tie_prone(8 * u + v)) {
+                        nx[v] = exq.embed(x[8 * u + v], (wA[i >> 5] >> (31 - (i & 31))) & 1u, (wB[i >> 5] >> (31 - (i & 31))) & 1u);
+                    } else if (i >= 0 && (NFULL || i < n)) {
                         const P2 y = fma2(x[8 * u + v], r2, ke);
                         uint32_t ya, yb;
                         unpk(y, ya, yb);
@@ -562,6 +607,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
     const P2 rr = pk(a.q.r, a.q.r), kx = pk(a.q.kx, a.q.kx);
     const uint32_t xmask = a.q.xmask;
     const int xk = a.q.xk;
+    const ExactQ exq = make_exact_q(G.delta32, a.q.r, a.q.negzero);
 
     constexpr int P = CH == 3 ? 3 : 1;
     uint2 rawA[8 * P], rawB[8 * P];
@@ -606,7 +652,12 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
                     const int i = 8 * u + v - 1;
-                    if (i >= 0 && (NFULL || i < n)) {
+                    if (i >= 0 && (NFULL || i < n) && tie_prone(8 * u + v)) {
+                        uint32_t ma, mb;                         // parity = lowest mantissa bit
+                        unpk(exq.rint_quotient_plus_magic(x[8 * u + v]), ma, mb);
+                        rowA |= (ma & 1u) << (7 - v);
+                        rowB |= (mb & 1u) << (7 - v);
+                    } else if (i >= 0 && (NFULL || i < n)) {
                         const P2 y = fma2(x[8 * u + v], rr, kx);
                         uint32_t ya, yb;
                         unpk(y, ya, yb);
