@@ -43,6 +43,18 @@ def algorithmic_bytes(frames, cap_bits):
     return frames * (3 * px + px + nb), frames * (px + nb)
 
 
+def fp32_pipe_roofline(frames, embed_ms, clocks):
+    """FP32-pipe lane operations the op-exact embed kernel must issue vs the pipe's peak."""
+    blocks = (H // 8) * (W // 8)
+    lane_ops = frames * blocks * (32 * 54 + 2 * min(NUM_AC, 63) + 64)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 128 * sm_mhz * 1e6
+    ach = lane_ops / (embed_ms / 1000.0)
+    return {"bound": "fp32 issue (secondary; not an HBM or tensor bound)", "kernel": "embed_kernel<3,1>",
+            "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T lane-op/s", "frac": ach / peak,
+            "lane_ops_per_block": 32 * 54 + 2 * min(NUM_AC, 63) + 64}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -415,6 +427,10 @@ def main():
                              "unit": "GB/s", "frac": ach_x / peak, "algorithmic_bytes_per_launch": xb,
                              "launch_ms": extract_ms},
         "roofline_round_trip": {"achieved": ach_rt, "peak": peak, "unit": "GB/s", "frac": ach_rt / peak},
+        # the co-limiter the HBM fraction has to be read with: reproducing scipy's float32 DCT bit for bit
+        # takes 54 un-fused FP32 operations per 8-point transform (no FMA contraction), i.e.
+        # 32 transforms x 54 + 63 x 2 + 64 per block for embed; peak = SMs x 128 lanes x SM clock
+        "roofline_fp32_pipe": fp32_pipe_roofline(F, embed_ms, clocks),
         "allgather": None if world == 1 else (
             "fused into extract_kernel: %s over NVLink into symmetric memory, barrier after each launch" % fused.mode
             if fused is not None else
@@ -486,6 +502,9 @@ def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world
     return {"value": world * F * steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": F * (3 * px + nbytes + px), "d2h_bytes_per_step": F * (px + nbytes),
             "steps": steps, "ms_per_step": 1000.0 * dt / steps, "parity_check": ok,
+            # what bounds it: the host<->device link, not the kernels (both directions run concurrently)
+            "pcie_h2d_gbs": F * (3 * px + nbytes + px) * steps / dt / 1e9,
+            "pcie_d2h_gbs": F * (px + nbytes) * steps / dt / 1e9,
             "api": "svs_embed_frames_host + svs_extract_frames_host (C ABI, pinned host buffers, 3-stream chunk pipeline)"}
 
 

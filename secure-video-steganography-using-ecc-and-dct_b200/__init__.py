@@ -10,9 +10,10 @@ from .frame_path import (proses_frame_qim_dct, install, embed_frames, extract_fr
                          bits_row_bytes, psnr_from_sse, EmbedResult, MAX_AC)
 
 from . import sharding
+from . import pipeline
 
 __all__ = [
-    "sharding",
+    "sharding", "pipeline",
     "build", "lib", "LIB_PATH", "EXPORTED_SYMBOLS", "SvsError",
     "bits_from_str", "bits_to_str", "pack_bits", "unpack_bits", "pack_str", "bytes_to_bitstring",
     "bitstring_to_bytes", "proses_frame_qim_dct", "install", "embed_frames", "extract_frames",
