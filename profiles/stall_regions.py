@@ -11,7 +11,8 @@ isrc, iex, ismp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.i
 names = ["stall_barrier", "stall_long_sb", "stall_math", "stall_no_inst", "stall_not_selected", "stall_selected",
          "stall_short_sb", "stall_wait", "stall_dispatch", "stall_lg", "stall_branch_resolving", "stall_mio"]
 idx = [hdr.index(n) for n in names]
-body = rows[2:2 + (len(rows) - 2) // 2]
+need = max([iex, ismp] + idx)
+body = [r for r in rows[2:2 + (len(rows) - 2) // 2] if len(r) > need]
 print("%-12s %10s %8s  " % ("lines", "executed", "samples") + " ".join("%7s" % n.replace("stall_", "")[:7] for n in names))
 tot = [0] * len(names)
 for s in range(0, len(body), chunk):
