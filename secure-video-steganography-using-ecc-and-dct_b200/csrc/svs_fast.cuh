@@ -491,6 +491,12 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     Lane L = locate_or_idle(G, (long long)blockIdx.x * kFastWarps + warp, lane, live);
     load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
     load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
+#ifdef SVS_EARLY_GRAY
+    // block A's gray bytes are made at the END of the previous group (its raw words arrived long
+    // before): 16 instead of 48 live registers across the top of the loop, where pressure peaks
+    uint32_t gA[16];
+    raw_to_gray<CH>(rawA, gA);
+#endif
 
     unsigned iter = 0;
     (void)iter;
@@ -507,8 +513,12 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
 
         P2 x[64];
         {
+#ifdef SVS_EARLY_GRAY
+            uint32_t gB[16];
+#else
             uint32_t gA[16], gB[16];
             raw_to_gray<CH>(rawA, gA);
+#endif
             raw_to_gray<CH>(rawB, gB);
             column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
             column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
@@ -581,6 +591,16 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
         uint8_t* dstB = out + (long long)(L.byB * 8) * a.stego_row_stride + L.bxB * (8 * OUT_CH);
         const bool okA = L.okA, okB = L.okB;
         L = locate_or_idle(G, g0 + gstep + warp, lane, live);          // the next group of this warp
+#ifndef SVS_NO_PAYLOAD_PREFETCH
+        {   // its payload words are consumed right after they are loaded (top of the next group): pull
+            // the two cache lines of the lane's blocks into L1 now, a whole output phase ahead
+            const long long at = a.payload_bit_offset + L.f * a.cap;
+            const long long wa = min((at + (long long)L.bA * n) >> 5, a.payload_last_word);
+            const long long wb = min((at + (long long)L.bB * n) >> 5, a.payload_last_word);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.payload + wa));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.payload + wb));
+        }
+#endif
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             svs::dct8_inv<1>(ops, x + 8 * r);
@@ -613,6 +633,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
             if (r == 5) load_block_rows<CH, 5, 8>(G, L.f, L.byB, L.bxB, rawB);
 #endif
         }
+#ifdef SVS_EARLY_GRAY
+        raw_to_gray<CH>(rawA, gA);
+#endif
     }
 }
 
