@@ -458,7 +458,10 @@ def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world
     """Same round trip through svs_*_frames_host: pinned host buffers, copies inside the timing."""
     import ctypes
     L = svs_b200.lib()
-    F = frames.shape[0]
+    # a third of the device batch per step (600 frames = 5.1 GB of pinned host memory per rank): the
+    # link-bound rate does not depend on the batch size, the host memory of an 8-rank box does
+    F = min(frames.shape[0], int(os.environ.get("SVS_BENCH_E2E_FRAMES", "600")))
+    frames, payload = frames[:F], payload[:F * nbytes]
     steps = max(1, min(args.steps, int(os.environ.get("SVS_BENCH_E2E_STEPS", "3"))))
     try:
         h_frames = torch.empty(frames.shape, dtype=torch.uint8).pin_memory()
@@ -501,7 +504,7 @@ def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world
     px = H * W
     return {"value": world * F * steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": F * (3 * px + nbytes + px), "d2h_bytes_per_step": F * (px + nbytes),
-            "steps": steps, "ms_per_step": 1000.0 * dt / steps, "parity_check": ok,
+            "steps": steps, "frames_per_step_per_gpu": F, "ms_per_step": 1000.0 * dt / steps, "parity_check": ok,
             # what bounds it: the host<->device link, not the kernels (both directions run concurrently)
             "pcie_h2d_gbs": F * (3 * px + nbytes + px) * steps / dt / 1e9,
             "pcie_d2h_gbs": F * (px + nbytes) * steps / dt / 1e9,
