@@ -388,6 +388,34 @@ __device__ __forceinline__ Lane locate(const FastGeom& G, long long g, int lane)
     return L;
 }
 
+// The same from (frame, first block of the group) with a multiply-high instead of the divisions:
+// cheap enough to be recomputed where it is needed instead of being kept (and spilled) across
+// a whole group.  Needs bpf * bw < 2^32 (host-checked).
+__device__ __forceinline__ Lane relocate(const FastGeom& G, int f, int base, int lane, bool live)
+{
+    Lane L;
+    L.f = f;
+    L.base = base;
+    const int last = G.bpf - 1;
+    L.okA = live && base + lane <= last;
+    L.okB = live && base + 32 + lane <= last;
+    L.bA = min(base + lane, last);
+    L.bB = min(base + 32 + lane, last);
+    L.byA = (int)__umulhi((unsigned)L.bA, G.bw_magic);
+    L.bxA = L.bA - L.byA * G.bw;
+    L.byB = (int)__umulhi((unsigned)L.bB, G.bw_magic);
+    L.bxB = L.bB - L.byB * G.bw;
+    return L;
+}
+__device__ __forceinline__ void group_of(const FastGeom& G, long long g, int& f, int& base, bool& live)
+{
+    live = g < G.total_groups;
+    const unsigned gi = (unsigned)(live ? g : G.total_groups - 1);
+    const unsigned ff = gi / (unsigned)G.groups_per_frame;
+    f = (int)ff;
+    base = (int)(gi - ff * (unsigned)G.groups_per_frame) * 64;
+}
+
 // Raw row words of one block of the lane (8 rows x P 8-byte words) -> registers.
 template <int CH>
 __device__ __forceinline__ void load_block_raw(const FastGeom& G, int f, int by, int bx, uint2* raw)
@@ -488,9 +516,19 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     uint2 rawA[8 * P], rawB[8 * P];
     const long long gstep = (long long)gridDim.x * kFastWarps;
     bool live;
+#ifdef SVS_RECOMPUTE_LANE
+    int cf, cbase;                       // all that is carried across a group: frame and first block
+    group_of(G, (long long)blockIdx.x * kFastWarps + warp, cf, cbase, live);
+    {
+        const Lane L = relocate(G, cf, cbase, lane, live);
+        load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
+        load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
+    }
+#else
     Lane L = locate_or_idle(G, (long long)blockIdx.x * kFastWarps + warp, lane, live);
     load_block_raw<CH>(G, L.f, L.byA, L.bxA, rawA);
     load_block_raw<CH>(G, L.f, L.byB, L.bxB, rawB);
+#endif
 #ifdef SVS_EARLY_GRAY
     // block A's gray bytes are made at the END of the previous group (its raw words arrived long
     // before): 16 instead of 48 live registers across the top of the loop, where pressure peaks
@@ -502,6 +540,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     (void)iter;
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
         SVS_LOCKSTEP();                        // keep the warps of the CTA in one instruction-cache window
+#ifdef SVS_RECOMPUTE_LANE
+        Lane L = relocate(G, cf, cbase, lane, live);
+#endif
         if (live && L.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[L.f] = a.cap;
 #ifdef SVS_L2_PREFETCH
         {
@@ -586,11 +627,22 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
         for (int v = 0; v < 8; ++v) svs::dct8_inv<8>(ops, x + v);
 
         SVS_LOCKSTEP2();
+#ifdef SVS_RECOMPUTE_LANE
+        asm volatile("" : "+r"(cbase));                                // recompute, do not keep
+        L = relocate(G, cf, cbase, lane, live);
+        uint8_t* out = a.stego + L.f * a.stego_frame_stride;
+        uint8_t* dstA = out + (long long)(L.byA * 8) * a.stego_row_stride + L.bxA * (8 * OUT_CH);
+        uint8_t* dstB = out + (long long)(L.byB * 8) * a.stego_row_stride + L.bxB * (8 * OUT_CH);
+        const bool okA = L.okA, okB = L.okB;
+        group_of(G, g0 + gstep + warp, cf, cbase, live);               // the next group of this warp
+        L = relocate(G, cf, cbase, lane, live);
+#else
         uint8_t* out = a.stego + L.f * a.stego_frame_stride;
         uint8_t* dstA = out + (long long)(L.byA * 8) * a.stego_row_stride + L.bxA * (8 * OUT_CH);
         uint8_t* dstB = out + (long long)(L.byB * 8) * a.stego_row_stride + L.bxB * (8 * OUT_CH);
         const bool okA = L.okA, okB = L.okB;
         L = locate_or_idle(G, g0 + gstep + warp, lane, live);          // the next group of this warp
+#endif
 #ifndef SVS_NO_PAYLOAD_PREFETCH
         {   // its payload words are consumed right after they are loaded (top of the next group): pull
             // the two cache lines of the lane's blocks into L1 now, a whole output phase ahead
