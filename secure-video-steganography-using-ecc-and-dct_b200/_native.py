@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
+HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_quant.h"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
            os.path.join(_PKG, "csrc", "svs_tile.cuh"), os.path.join(_PKG, "csrc", "svs_row.cuh"),
            os.path.join(_ROOT, "include", "svs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -23,6 +23,7 @@
 
 #include "svs_b200.h"
 #include "svs_math.cuh"
+#include "svs_quant.h"
 #include "svs_fast.cuh"
 #include "svs_tile.cuh"
 #include "svs_row.cuh"
@@ -406,47 +407,7 @@ void launch_extract(const ExtractArgs& a, bool words, unsigned grid, cudaStream_
 }
 
 
-// Constants of the division-free quantiser (svs_fast.cuh).  |c| <= 2040 for any 8x8 block of
-// bytes (orthonormal basis, L1 norm <= 8), so x = c/(2 delta) + 1/4 (embed) and c/delta + 1/2
-// (extract) are bounded and M = 1.5 * 2^(23-k) leaves k fraction bits in the mantissa of M + x.
-// Error budget (units of 2^-k): rounding of the FMA 1/2, reciprocal instead of division 1/4,
-// the reference's own quotient rounding 1/4 -> strictly below 1; the kernels flag 2.
-fast::FastQuant make_fast_quant(double delta)
-{
-    fast::FastQuant q;
-    memset(&q, 0, sizeof q);
-    q.negzero = -0.0f;
-    const float d32 = (float)delta;
-    if (!(delta >= 0x1p-4) || !(delta <= 0x1p20)) return q;
-    {
-        const double xmax = 1020.0 / d32 + 1.5;
-        int k = 22 - (int)std::ceil(std::log2(xmax + 1.0));
-        if (k > 20) k = 20;
-        const double M = 1.5 * std::ldexp(1.0, 23 - k);
-        q.r2 = (float)(0.5 / (double)d32);
-        q.ke = (float)(M + 0.25 + 2.0 * std::ldexp(1.0, -k));
-        q.d2 = 2.0f * d32;
-        const double k0 = -(double)q.d2 * M;
-        q.k0 = (float)k0;
-        q.emask = (1u << k) - 1u;
-        q.ebit = 1u << (k - 1);
-        q.erot = k - 1;
-        q.embed_ok = k >= 8 && (double)q.k0 == k0 && (double)d32 == delta &&
-                     (double)q.ke == M + 0.25 + 2.0 * std::ldexp(1.0, -k);
-    }
-    {
-        const double xmax = 2040.0 / d32 + 1.5;
-        int k = 22 - (int)std::ceil(std::log2(xmax + 1.0));
-        if (k > 20) k = 20;
-        const double M = 1.5 * std::ldexp(1.0, 23 - k);
-        q.r = (float)(1.0 / (double)d32);
-        q.kx = (float)(M + 0.5 + 2.0 * std::ldexp(1.0, -k));
-        q.xmask = (1u << k) - 1u;
-        q.xk = k;
-        q.extract_ok = k >= 8 && (double)q.kx == M + 0.5 + 2.0 * std::ldexp(1.0, -k);
-    }
-    return q;
-}
+using svs::make_fast_quant;     // svs_quant.h
 
 fast::FastGeom make_fast_geometry(const Geometry& g, long long n_frames)
 {

@@ -75,19 +75,7 @@ struct PackedOps {
     __device__ __forceinline__ T mulc(T a, float c) const { return fma2(a, pk(c, c), negzero); }
 };
 
-// Host-computed constants of the division-free quantiser (see make_fast_quant in svs_b200.cu).
-struct FastQuant {
-    // embed: y = fma(c, r2, ke) = M + floor(c/(2 delta) + 1/4) + fraction, k fraction bits
-    float r2, ke, d2, k0;
-    uint32_t emask, ebit;           // 2^k - 1, 1 << (k-1)
-    int erot;                       // k - 1: where the payload bit is inserted (value 1/2)
-    // extract: y = fma(c, r, kx) = M + floor(c/delta + 1/2) + fraction; bit xk is the parity
-    float r, kx;
-    uint32_t xmask;
-    int xk;
-    float negzero;                  // -0.0f, opaque to the compiler
-    int embed_ok, extract_ok;
-};
+using svs::FastQuant;            // host-computed constants of the division-free quantiser (svs_quant.h)
 
 // One CTA per SM, 12 warps, 64 blocks (2 per thread) per warp and per loop iteration.  168
 // registers per thread x 384 threads fills the register file; the CTA is persistent and strides

@@ -11,11 +11,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "host_math.cpp")
 HDR = os.path.join(ROOT, "secure-video-steganography-using-ecc-and-dct_b200", "csrc", "svs_math.cuh")
+HDR2 = os.path.join(os.path.dirname(HDR), "svs_quant.h")
 OUT = os.path.join(HERE, "_build", "libhost_math.so")
 
 
 def build():
-    if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+    if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2)):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
@@ -28,4 +29,6 @@ def load():
     for name in ("hm_dct2_fwd", "hm_dct2_inv", "hm_dct8_fwd", "hm_dct8_inv"):
         getattr(L, name).restype = None
         getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_long]
+    L.hm_quant_check.restype = None
+    L.hm_quant_check.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
     return L

@@ -115,6 +115,37 @@ def test_kernel_arithmetic_host_build_matches_oracle():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("delta", [0.0625, 0.5, 1, 2, 2.5, 3, 4, 6, 7, 8, 10, 16, 20, 32, 50, 64, 100, 1000])
+def test_quantiser_claims_against_the_ieee_division(delta):
+    """csrc/svs_quant.h: the division-free quantiser only ever differs from the reference's
+    round(c / delta) (config_and_setup.py:148,160) on coefficients it flags for the exact path, and
+    the exact path (rounded reciprocal + two Newton steps + magic-constant rint) never differs -
+    on random coefficients, on multiples of 1/8 (what (0,4),(4,0),(4,4) produce), on exact rounding
+    ties and on their float32 neighbours."""
+    L = hm.load()
+    rng = np.random.default_rng(int(delta * 16))
+    d32 = np.float32(delta)
+    ties = ((np.arange(-3000, 3000) + 0.5) * float(d32)).astype(np.float32)
+    ties = ties[np.abs(ties) <= 2040]
+    near = np.concatenate([np.nextafter(ties, np.float32(np.inf)), np.nextafter(ties, np.float32(-np.inf)),
+                           np.nextafter(np.nextafter(ties, np.float32(np.inf)), np.float32(np.inf))])
+    c = np.concatenate([rng.uniform(-2040, 2040, 300000).astype(np.float32),
+                        (rng.integers(-16320, 16321, 100000) / 8.0).astype(np.float32),
+                        (rng.standard_normal(100000) * 40).astype(np.float32), ties, near,
+                        np.array([0.0, -0.0, 2040.0, -2040.0], np.float32)])
+    c = np.ascontiguousarray(c)
+    stats = np.zeros(8, np.int64)
+    L.hm_quant_check(float(delta), c.ctypes.data, c.size, stats.ctypes.data)
+    flagged_e, flagged_x, bad_fast_e, bad_fast_x, bad_exact_e, bad_exact_x, embed_ok, extract_ok = stats.tolist()
+    assert embed_ok and (extract_ok or delta < 0.25)   # these deltas take the packed kernels
+    assert bad_fast_e == 0 and bad_fast_x == 0, stats
+    assert bad_exact_e == 0 and bad_exact_x == 0, stats
+    if extract_ok:
+        assert flagged_x >= ties.size * 0.9            # every exact tie is sent to the exact path
+    if delta >= 4:                                     # (small deltas make the constructed ties a large share)
+        assert flagged_e + flagged_x < 0.1 * c.size    # ... and the flag stays rare
+
+
 def test_psnr_from_sse():
     assert svs_b200.psnr_from_sse(0, 8, 8) == float("inf")
     assert abs(svs_b200.psnr_from_sse(64, 8, 8) - 20 * np.log10(255.0)) < 1e-9
