@@ -179,6 +179,48 @@ def test_bgr_stego_store_and_strided_views(kernel_family):
     assert np.array_equal(want, ext)
 
 
+@pytest.mark.parametrize("shape,n", [((3, 64, 128, 3), 63), ((2, 72, 256, 3), 20), ((2, 64, 128), 63)])
+def test_bgr_stego_store_contiguous_batches(shape, n, kernel_family):
+    """N2 on 16-byte aligned, contiguous batches (what every packed family accepts): the 3-channel
+    stego equals the gray stego of the oracle in all channels, and extracting from it returns the
+    same bits as extracting from the gray stego."""
+    frames = synth_frames("bgrout%s" % (shape,), shape, 20, 236)
+    h, w = shape[1:3]
+    delta = 20
+    cap = svs_b200.capacity_bits(h, w, n)
+    bits = synth_bits("bgrout", shape[0] * cap)
+    res = svs_b200.embed_frames(_dev(frames), _dev(np.packbits(bits)), bits.size, delta, n, stego_channels=3)
+    stego, _, _ = oc.embed_frames(frames, np.packbits(bits), bits.size, delta, n)
+    got = res.stego.cpu().numpy()
+    assert got.shape == shape[:3] + (3,)
+    for ch in range(3):
+        _assert_same_pixels(stego, got[..., ch], "BGR stego channel %d" % ch)
+    ext3 = svs_b200.extract_frames(res.stego, delta, n).cpu().numpy()
+    assert np.array_equal(ext3, oc.extract_frames(stego, delta, n))
+
+
+@pytest.mark.parametrize("family", ["lockstep", "row"])
+def test_extract_with_peer_scatter_on_one_device(family):
+    """svs_extract_frames_scatter with "peers" that are further buffers on the same GPU: every
+    buffer receives the rows (the 2-GPU NVLink variant is tests/test_multi_gpu.py)."""
+    torch = _torch()
+    prev = svs_b200.lib().svs_debug_force_scalar({"lockstep": 2, "row": 4}[family])
+    try:
+        frames = synth_frames("scatter", (5, 64, 128), 0, 256)
+        n, delta = 63, 20
+        pitch = svs_b200.bits_row_bytes(64, 128, n)
+        bufs = [torch.zeros((5, pitch), dtype=torch.uint8, device="cuda") for _ in range(4)]
+        got = svs_b200.extract_frames(_dev(frames), delta, n, out=bufs[0], peer_ptrs=[b.data_ptr() for b in bufs[1:]])
+        want = oc.extract_frames(frames, delta, n)
+        assert np.array_equal(got.cpu().numpy(), want)
+        for b in bufs[1:]:
+            assert torch.equal(b, bufs[0])
+        with pytest.raises(ValueError):                       # 16 peers: more than the kernels take
+            svs_b200.extract_frames(_dev(frames), delta, n, out=bufs[0], peer_ptrs=[bufs[1].data_ptr()] * 16)
+    finally:
+        svs_b200.lib().svs_debug_force_scalar(prev)
+
+
 def test_extract_byte_store_path_matches_word_store_path():
     """bits_frame_stride == ceil(cap/8) (not a multiple of 4) exercises the byte-store kernel."""
     torch = _torch()
