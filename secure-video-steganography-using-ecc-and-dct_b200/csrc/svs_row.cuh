@@ -1,4 +1,4 @@
-// svs_row.cuh - "row" throughput kernels of the DCT-QIM path (included by svs_b200.cu).
+// svs_row.cuh - "row" kernels of the DCT-QIM path (included by svs_b200.cu); kernel family 4.
 //
 // Same arithmetic and same results as svs_fast.cuh, bit for bit (packed FADD2/FFMA2 transforms in
 // scipy's operation order, division-free quantiser with the exact out-of-line fallback), but the
@@ -9,17 +9,24 @@
 //   * between the passes the 8x8 tile is transposed through a warp-private, padded (conflict
 //     free) shared-memory tile: three 64-bit transposes per embed, one per extract, plus one byte
 //     transpose of the gray input; only __syncwarp is ever needed;
-//   * the whole loop body is ~600 instructions (10 KB): it fits the 32 KB L1.5 instruction cache,
-//     so the warps of an SM run FREE (svs_fast.cuh is 4 k instructions and has to keep its 12
-//     warps in lockstep with a bar.sync per group, which serialises its load / FP32 / ALU phases);
-//   * ~64 registers per thread -> 32 resident warps per SM hide the HBM and shared-memory latency
-//     by themselves; the next tile's input is still loaded one tile ahead (4 or 12 registers);
+//   * the loop body is ~650 instructions (10 KB): it fits the 32 KB L1.5 instruction cache, so
+//     the warps of an SM run FREE (svs_fast.cuh is 4 k instructions and has to keep its 12 warps
+//     in lockstep with a bar.sync per group, which serialises its load / FP32 / ALU phases);
+//   * 64-80 registers per thread -> 24-32 resident warps per SM; the next tile's input and
+//     payload words are still requested one tile ahead;
 //   * a lane reads 16 (gray) or 48 (BGR) contiguous bytes with LDG.128 and writes its stego row of
 //     both blocks with one STG.128.
 // One warp = 4 block pairs = 8 consecutive blocks (64 x 8 pixels) per tile, 8 tiles per 64-block
 // group (so that the extracted bits of a group start on an 8-byte boundary, as in svs_fast.cuh).
-// Needs an even number of blocks per row (W % 16 == 0) and 16-byte aligned rows; everything else
-// goes to the other kernel families.
+// Needs an even number of blocks per row (W % 16 == 0, W >= 64) and 16-byte aligned rows;
+// everything else goes to the other kernel families.
+//
+// MEASURED (B200, 600 x 1080p, DESIGN.md section 4 / profiles/r1_row_variant_summary.txt): embed
+// 2.43 ms, extract 1.26 ms against 1.84 / 0.83 ms for the lockstep kernels.  The transposes, the
+// per-16-pixel bookkeeping and the run-time row index cost 35 % more issue slots per pixel and the
+// free-running warps reach 58 % issue utilisation (short-scoreboard / MIO stalls on the
+// transposes), so this family is NOT the default; it is kept because it is parity-green (every
+// parity test runs it) and is the reference point for the alternative organisation.
 #pragma once
 
 namespace row {
