@@ -55,6 +55,34 @@ def fp32_pipe_roofline(frames, embed_ms, clocks):
             "lane_ops_per_block": 32 * 54 + 2 * min(NUM_AC, 63) + 64}
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Multi-rank runs: keep the rank (and with it the first-touch placement of its pinned host
+    buffers) on the CPUs NVML reports as local to its GPU, so that the e2e copies do not cross the
+    socket interconnect.  Best effort; returns the number of CPUs bound to (0 = left alone)."""
+    if os.environ.get("SVS_BENCH_NUMA_BIND", "1") == "0":
+        return 0
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            tok = vis.split(",")[device_index].strip()
+            h = pynvml.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -252,6 +280,7 @@ def main():
     # into every rank's gathered buffer over NVLink (symmetric memory; multicast when available),
     # "nccl" = chunked extract + ncclAllGather overlapped on a side stream, "nccl-seq" = plain all-gather
     gather_mode = os.environ.get("SVS_GATHER", "push") if world > 1 else "none"
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0     # (N = 1 keeps all cores for cpu_baseline)
     if world > 1:
         reserved = int(os.environ.get("SVS_RESERVED_SMS", "8")) if gather_mode == "nccl" else 0
         if gather_mode == "nccl":
@@ -418,7 +447,8 @@ def main():
                                               "nccl": " + NCCL all-gather of bits (chunked, overlapped on a side stream)",
                                               "nccl-seq": " + NCCL all-gather of bits"}[gather_mode],
                    "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % ((eb + xb) / 1e9),
-                   "parallelism": "frame-sharded x%d" % world},
+                   "parallelism": "frame-sharded x%d" % world,
+                   "host": "rank bound to the %d CPUs local to its GPU" % numa_cpus if numa_cpus else "no CPU binding"},
         "mpixel_per_s": value * H * W / 1e6,
         "roofline": {"bound": "hbm", "kernel": "embed_kernel<3,1>", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
