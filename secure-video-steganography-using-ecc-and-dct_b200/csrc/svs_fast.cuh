@@ -92,6 +92,18 @@ constexpr int kFastWarps = kFastThreads / 32;
 #ifndef SVS_SYNC_EVERY
 #define SVS_SYNC_EVERY 1
 #endif
+// Skewed lockstep (experiment, OFF by default).  In strict lockstep the three warps that share an
+// SM sub-partition (warp % 4) run the same phase at the same time - all in an FP32-heavy
+// transform, then all in the ALU-heavy quantiser.  With SVS_SKEW=1 the three "slots" (warp / 4)
+// arrive at the SAME group barrier from three different places of the instruction stream, about a
+// third of a row period (~50 instructions) apart, so that one warp's quantiser could run under
+// the other two warps' transforms at no cost in instruction-cache footprint.  MEASURED: slower
+// (embed 2.13 vs 1.85 ms, extract 0.85 vs 0.83 ms per 600 frames; 44 B more spills) - the phases
+// of a single warp already interleave well enough and the mid-stream arrivals only add stalls.
+#ifndef SVS_SKEW
+#define SVS_SKEW 0
+#endif
+#define SVS_ARRIVE(site, on) do { if ((on) && (SVS_SKEW ? slot == (site) : (site) == 0)) asm volatile("bar.sync 0;" ::: "memory"); } while (0)
 #define SVS_LOCKSTEP() do { if (SVS_SYNC_LEVEL >= 1 && (SVS_SYNC_EVERY == 1 || (iter++ % SVS_SYNC_EVERY) == 0)) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP2() do { if (SVS_SYNC_LEVEL >= 2) __syncthreads(); } while (0)
 #define SVS_LOCKSTEP3() do { if (SVS_SYNC_LEVEL >= 3) __syncthreads(); } while (0)
@@ -456,6 +468,20 @@ __device__ __forceinline__ void raw_to_gray(const uint2* raw, uint32_t (&g)[16])
     for (int r = 0; r < 8; ++r) row_to_gray<CH>(raw + r * P, g[2 * r], g[2 * r + 1]);
 }
 
+// raw_to_gray of the first block with the barrier arrivals of slots 1 and 2 inside (BGR input:
+// 22 instructions per row, so rows 2 and 4 are ~44 and ~88 instructions after the loop top).
+template <int CH>
+__device__ __forceinline__ void raw_to_gray_arrive(const uint2* raw, uint32_t (&g)[16], int slot, bool on)
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        row_to_gray<CH>(raw + r * P, g[2 * r], g[2 * r + 1]);
+        if (CH == 3 && r == 1) SVS_ARRIVE(1, on);
+        if (CH == 3 && r == 3) SVS_ARRIVE(2, on);
+    }
+}
+
 // The lane's blocks for group g; warps past the end of the work redo the last group with their
 // stores masked so that every warp of the CTA executes the same instruction stream.
 __device__ __forceinline__ Lane locate_or_idle(const FastGeom& G, long long g, int lane, bool& live)
@@ -489,6 +515,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
 {
     const FastGeom& G = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = min(warp >> 2, 2);            // which of the warps of its SM sub-partition this is
     const int n = NFULL ? 63 : G.n;
     PackedOps ops;
     ops.negzero = pk(a.q.negzero, a.q.negzero);
@@ -527,7 +554,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
     unsigned iter = 0;
     (void)iter;
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
-        SVS_LOCKSTEP();                        // keep the warps of the CTA in one instruction-cache window
+        SVS_ARRIVE(0, SVS_SYNC_LEVEL >= 1);    // keep the warps of the CTA in one instruction-cache window
 #ifdef SVS_RECOMPUTE_LANE
         Lane L = relocate(G, cf, cbase, lane, live);
 #endif
@@ -546,10 +573,13 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
             uint32_t gB[16];
 #else
             uint32_t gA[16], gB[16];
-            raw_to_gray<CH>(rawA, gA);
+            raw_to_gray_arrive<CH>(rawA, gA, slot, SVS_SYNC_LEVEL >= 1);
 #endif
             raw_to_gray<CH>(rawB, gB);
-            column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<0>(ops, gA, gB, G.magic_hi, x);
+            if (CH != 3) SVS_ARRIVE(1, SVS_SYNC_LEVEL >= 1);
+            column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            if (CH != 3) SVS_ARRIVE(2, SVS_SYNC_LEVEL >= 1);
             column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
             column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
             column_fwd<6>(ops, gA, gB, G.magic_hi, x); column_fwd<7>(ops, gA, gB, G.magic_hi, x);
@@ -688,6 +718,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
     __shared__ uint32_t pack[kFastWarps][128];
     const FastGeom& G = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = min(warp >> 2, 2);
     const int n = NFULL ? 63 : G.n;
     PackedOps ops;
     ops.negzero = pk(a.q.negzero, a.q.negzero);
@@ -707,16 +738,20 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
     unsigned iter = 0;
     (void)iter;
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
-        if ((iter++ & 3u) == 0) SVS_LOCKSTEP();          // small code: a loose lockstep is enough here
+        const bool sync_now = SVS_SYNC_LEVEL >= 1 && (iter++ & 3u) == 0;   // small code: a loose lockstep is enough
+        SVS_ARRIVE(0, sync_now);
 #pragma unroll
         for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
 
         P2 x[64];
         {
             uint32_t gA[16], gB[16];
-            raw_to_gray<CH>(rawA, gA);
+            raw_to_gray_arrive<CH>(rawA, gA, slot, sync_now);
             raw_to_gray<CH>(rawB, gB);
-            column_fwd<0>(ops, gA, gB, G.magic_hi, x); column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            column_fwd<0>(ops, gA, gB, G.magic_hi, x);
+            if (CH != 3) SVS_ARRIVE(1, sync_now);
+            column_fwd<1>(ops, gA, gB, G.magic_hi, x);
+            if (CH != 3) SVS_ARRIVE(2, sync_now);
             column_fwd<2>(ops, gA, gB, G.magic_hi, x); column_fwd<3>(ops, gA, gB, G.magic_hi, x);
             column_fwd<4>(ops, gA, gB, G.magic_hi, x); column_fwd<5>(ops, gA, gB, G.magic_hi, x);
             column_fwd<6>(ops, gA, gB, G.magic_hi, x); column_fwd<7>(ops, gA, gB, G.magic_hi, x);
