@@ -122,6 +122,8 @@ int svs_extract_frames_multicast(const uint8_t* d_frames, int channels, int64_t 
  *   d_bits_embedded_out  per-frame count of embedded bits (third return value)
  *   d_sse_out          per-frame sum of (stego-gray)^2 over all pixels, for PSNR
  *                      (embed_process.py:204-206); the caller must zero it beforehand.
+ *                      (gray / SSE of the frames the packed kernels take come from one extra
+ *                      streaming launch; the kernel launch count reflects it.)
  */
 int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
                      int height, int width, int64_t frame_stride, int64_t row_stride,

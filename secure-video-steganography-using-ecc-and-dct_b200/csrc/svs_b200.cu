@@ -334,6 +334,72 @@ __global__ void __launch_bounds__(kThreads, 4) extract_kernel(const ExtractArgs 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Side outputs of embed for the frames the packed kernels handle: the gray reference (first
+// return value of the reference function, config_and_setup.py:111-114,172) and the per-frame
+// sum of squared errors gray vs stego (what cv2.PSNR needs, embed_process.py:204-206).  The
+// packed embed kernels have no registers left for either, and a separate streaming pass
+// (4 + 1 bytes read, 1 written per pixel, pure HBM) on top of them is faster than the scalar
+// embed kernel that produces them in its epilogue.  16 pixels per thread, W % 16 == 0.
+// ------------------------------------------------------------------------------------------
+struct SideArgs {
+    const uint8_t* frames;
+    long long frame_stride, row_stride;
+    const uint8_t* stego;                   // 1 channel
+    long long stego_frame_stride, stego_row_stride;
+    uint8_t* gray;                          // nullable, contiguous frames
+    unsigned long long* sse;                // nullable
+    int H, W16;                             // rows, 16-pixel chunks per row
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) side_outputs_kernel(const SideArgs a)
+{
+    const long long f = blockIdx.y;
+    const int per_frame = a.H * a.W16;
+    unsigned sse = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += gridDim.x * blockDim.x) {
+        const int y = i / a.W16, c = i - y * a.W16;
+        const uint8_t* src = a.frames + f * a.frame_stride + (long long)y * a.row_stride + (long long)c * (16 * CH);
+        uint32_t g[4];
+        if (CH == 1) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+            g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+        } else {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+            const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src) + 2);
+            const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            row::bgr8_to_gray(w, g[0], g[1]);
+            row::bgr8_to_gray(w + 6, g[2], g[3]);
+        }
+        if (a.gray != nullptr)
+            *reinterpret_cast<uint4*>(a.gray + (f * a.H + y) * (long long)(a.W16 * 16) + c * 16) = make_uint4(g[0], g[1], g[2], g[3]);
+        if (a.sse != nullptr) {
+            const uint4 s = __ldg(reinterpret_cast<const uint4*>(a.stego + f * a.stego_frame_stride + (long long)y * a.stego_row_stride + c * 16));
+            const uint32_t sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t d = __vabsdiffu4(g[k], sv[k]);
+                sse = __dp4a(d, d, sse);                    // sum of the four squared byte differences
+            }
+        }
+    }
+    if (a.sse != nullptr) {
+        __shared__ unsigned long long part[8];
+        unsigned long long t = sse;                         // per thread < 2^32 (host caps the chunks per thread)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            t = 0;
+            for (int w = 0; w < 8; ++w) t += part[w];
+            if (t) atomicAdd(a.sse + f, t);
+        }
+    }
+}
+
 thread_local char g_err[256] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_reserved_sms{0};
@@ -720,7 +786,13 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     // Frames the payload fills completely go to the packed-FP32 kernel; the frame in which the
     // payload ends and everything after it (and every special case) to the scalar kernel.
     const fast::FastQuant fq = make_fast_quant(delta);
-    if (family() != 1 && al && !f64 && a.active && fq.embed_ok && d_gray_out == nullptr && d_sse_out == nullptr &&
+    // the optional gray / SSE outputs of those frames come from a separate streaming kernel when its
+    // 16-pixel accesses apply; otherwise such a call goes to the scalar kernel altogether
+    const bool want_side = d_gray_out != nullptr || d_sse_out != nullptr;
+    const bool side_ok = (width % 16) == 0 && aligned_to(d_frames, frame_stride, row_stride, 16) && stego_channels == 1 &&
+                         aligned_to(d_stego_out, stego_frame_stride, stego_row_stride, 16) &&
+                         (d_gray_out == nullptr || aligned_to(d_gray_out, 0, 0, 16)) && n_frames <= 65535;
+    if (family() != 1 && al && !f64 && a.active && fq.embed_ok && (!want_side || side_ok) &&
         n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
         long long full = payload_total_bits / a.cap;
         if (full > n_frames) full = n_frames;
@@ -778,6 +850,29 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             g_launches.fetch_add(1);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (packed)");
+            if (want_side) {
+                SideArgs sa;
+                sa.frames = d_frames;
+                sa.frame_stride = frame_stride;
+                sa.row_stride = row_stride;
+                sa.stego = d_stego_out;
+                sa.stego_frame_stride = stego_frame_stride;
+                sa.stego_row_stride = stego_row_stride;
+                sa.gray = d_gray_out;
+                sa.sse = d_sse_out;
+                sa.H = height;
+                sa.W16 = width / 16;
+                const int per_frame = height * (width / 16);
+                int gx = (per_frame + 255) / 256;
+                if (gx > 64) gx = 64;
+                if (per_frame / (gx * 256) > 4000) gx = per_frame / (256 * 4000) + 1;   // 32-bit per-thread sums: <= 4000 chunks each
+                const dim3 grid((unsigned)gx, (unsigned)full);
+                if (channels == 3) side_outputs_kernel<3><<<grid, 256, 0, st>>>(sa);
+                else side_outputs_kernel<1><<<grid, 256, 0, st>>>(sa);
+                g_launches.fetch_add(1);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (gray / SSE)");
+            }
             if (full == n_frames) return SVS_OK;
             // the remaining frames: shift every per-frame quantity by `full`
             a.g.frames += full * frame_stride;
@@ -785,6 +880,8 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             a.payload_total_bits -= full * a.cap;
             a.stego += full * stego_frame_stride;
             if (a.bits_embedded) a.bits_embedded += full;
+            if (a.gray) a.gray += full * (long long)height * width;
+            if (a.sse) a.sse += full;
             n_frames -= full;
         }
     }
