@@ -14,8 +14,9 @@
 //   * f32 -> u8 with saturation and truncation in one F2IP (cvt.rzi.u8.f32) on the otherwise
 //     idle conversion pipe - that is np.uint8(np.clip(v, 0, 255)), config_and_setup.py:171.
 // Only whole frames that the payload fills completely come here (k == n for every block); the
-// frame in which the payload ends, strided/unaligned inputs, non-float32 deltas and the optional
-// gray / SSE outputs are handled by the scalar kernels.
+// frame in which the payload ends, strided/unaligned inputs and non-float32 deltas are handled by
+// the scalar kernels; the optional gray / SSE outputs of the frames handled here come from the
+// streaming side_outputs_kernel in svs_b200.cu.
 #pragma once
 
 namespace fast {
