@@ -554,8 +554,22 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
 
     unsigned iter = 0;
     (void)iter;
+#ifdef SVS_SPLIT_BARRIER
+    // split-phase group barrier on an mbarrier: every warp ARRIVES at the top of the group and only
+    // WAITS after the gray conversion (~350 instructions later), so that the normal skew between the
+    // warps is absorbed instead of being paid as a stall, while they still share one cache window
+    __shared__ unsigned long long group_bar;
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&group_bar);
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(bar_addr), "r"(kFastWarps));
+    __syncthreads();
+    uint32_t bar_phase = 0;
+#endif
     for (long long g0 = (long long)blockIdx.x * kFastWarps; g0 < G.total_groups; g0 += gstep) {
+#ifdef SVS_SPLIT_BARRIER
+        if (lane == 0) asm volatile("{.reg .b64 t; mbarrier.arrive.shared.b64 t, [%0];}" ::"r"(bar_addr) : "memory");
+#else
         SVS_ARRIVE(0, SVS_SYNC_LEVEL >= 1);    // keep the warps of the CTA in one instruction-cache window
+#endif
 #ifdef SVS_RECOMPUTE_LANE
         Lane L = relocate(G, cf, cbase, lane, live);
 #endif
@@ -577,6 +591,12 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
             raw_to_gray_arrive<CH>(rawA, gA, slot, SVS_SYNC_LEVEL >= 1);
 #endif
             raw_to_gray<CH>(rawB, gB);
+#ifdef SVS_SPLIT_BARRIER
+            asm volatile("{.reg .pred p;\n"
+                         "SVS_WAIT_%=: mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+                         "@!p bra SVS_WAIT_%=;}" ::"r"(bar_addr), "r"(bar_phase) : "memory");
+            bar_phase ^= 1u;
+#endif
             column_fwd<0>(ops, gA, gB, G.magic_hi, x);
             if (CH != 3) SVS_ARRIVE(1, SVS_SYNC_LEVEL >= 1);
             column_fwd<1>(ops, gA, gB, G.magic_hi, x);
