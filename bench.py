@@ -50,7 +50,7 @@ def fp32_pipe_roofline(frames, embed_ms, clocks):
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak = 148 * 128 * sm_mhz * 1e6
     ach = lane_ops / (embed_ms / 1000.0)
-    return {"bound": "fp32 issue (secondary; not an HBM or tensor bound)", "kernel": "embed_kernel<3,1>",
+    return {"bound": "fp32 issue (secondary; not an HBM or tensor bound)", "kernel": "fast::embed_fast_kernel<3,1,true>",
             "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T lane-op/s", "frac": ach / peak,
             "lane_ops_per_block": 32 * 54 + 2 * min(NUM_AC, 63) + 64}
 
@@ -450,10 +450,10 @@ def main():
                    "parallelism": "frame-sharded x%d" % world,
                    "host": "rank bound to the %d CPUs local to its GPU" % numa_cpus if numa_cpus else "no CPU binding"},
         "mpixel_per_s": value * H * W / 1e6,
-        "roofline": {"bound": "hbm", "kernel": "embed_kernel<3,1>", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "fast::embed_fast_kernel<3,1,true>", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": eb, "launch_ms": embed_ms},
-        "roofline_extract": {"bound": "hbm", "kernel": "extract_kernel<1>", "achieved": ach_x, "peak": peak,
+        "roofline_extract": {"bound": "hbm", "kernel": "fast::extract_fast_kernel<1,true>", "achieved": ach_x, "peak": peak,
                              "unit": "GB/s", "frac": ach_x / peak, "algorithmic_bytes_per_launch": xb,
                              "launch_ms": extract_ms},
         "roofline_round_trip": {"achieved": ach_rt, "peak": peak, "unit": "GB/s", "frac": ach_rt / peak},
