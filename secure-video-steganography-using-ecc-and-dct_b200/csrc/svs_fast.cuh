@@ -508,6 +508,54 @@ __device__ __forceinline__ void column_fwd(const PackedOps& ops, const uint32_t 
     svs::dct8_fwd<8>(ops, x + C);
 }
 
+// Input stage for BGR frames: image row r of both blocks straight to its eight
+// packed floats, without packing the gray bytes into words first (BGR: the dp2a sums keep the
+// gray value in byte 2 and the PRMT that builds the 2^23 + gray float reads it from there), then
+// the eight column transforms.  96 PRMT fewer per 64-block group, no gA / gB arrays.
+template <int CH>
+__device__ __forceinline__ void row_to_x(const uint2* wa, const uint2* wb, uint32_t magic_hi, P2* xr)
+{
+    const P2 unbias = pk(-8388608.0f, -8388608.0f);
+    if (CH == 1) {
+        const uint32_t a[2] = {wa[0].x, wa[0].y}, b[2] = {wb[0].x, wb[0].y};
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            xr[c] = add2(pku(__byte_perm(a[c >> 2], magic_hi, 0x7540 | (c & 3)), __byte_perm(b[c >> 2], magic_hi, 0x7540 | (c & 3))), unbias);
+    } else {
+        constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
+        const uint32_t va[6] = {wa[0].x, wa[0].y, wa[1].x, wa[1].y, wa[2].x, wa[2].y};
+        const uint32_t vb[6] = {wb[0].x, wb[0].y, wb[1].x, wb[1].y, wb[2].x, wb[2].y};
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+            const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
+            uint32_t sa, sb;
+            if (off == 0) {
+                sa = __dp2a_hi(WR, va[wi], __dp2a_lo((WG << 16) | WB, va[wi], RND));
+                sb = __dp2a_hi(WR, vb[wi], __dp2a_lo((WG << 16) | WB, vb[wi], RND));
+            } else if (off == 1) {
+                sa = __dp2a_hi((WR << 16) | WG, va[wi], __dp2a_lo(WB << 16, va[wi], RND));
+                sb = __dp2a_hi((WR << 16) | WG, vb[wi], __dp2a_lo(WB << 16, vb[wi], RND));
+            } else if (off == 2) {
+                sa = __dp2a_lo(WR, va[wi + 1], __dp2a_hi((WG << 16) | WB, va[wi], RND));
+                sb = __dp2a_lo(WR, vb[wi + 1], __dp2a_hi((WG << 16) | WB, vb[wi], RND));
+            } else {
+                sa = __dp2a_lo((WR << 16) | WG, va[wi + 1], __dp2a_hi(WB << 16, va[wi], RND));
+                sb = __dp2a_lo((WR << 16) | WG, vb[wi + 1], __dp2a_hi(WB << 16, vb[wi], RND));
+            }
+            xr[px] = add2(pku(__byte_perm(sa, magic_hi, 0x7542), __byte_perm(sb, magic_hi, 0x7542)), unbias);   // exact
+        }
+    }
+}
+template <int CH>
+__device__ __forceinline__ void input_rowwise(const PackedOps& ops, const uint2* rawA, const uint2* rawB, uint32_t magic_hi, P2 (&x)[64])
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) row_to_x<CH>(rawA + r * P, rawB + r * P, magic_hi, x + 8 * r);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) svs::dct8_fwd<8>(ops, x + c);
+}
+
 // ------------------------------------------------------------------------------------------
 // embed: every block of every frame handled here is completely filled with payload (k == n)
 // ------------------------------------------------------------------------------------------
@@ -583,6 +631,13 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) embed_fast_kerne
 #endif
 
         P2 x[64];
+#ifndef SVS_COLUMNWISE_INPUT
+        if (CH == 3) {                             // BGR: row-wise, no packed gray words (1 % faster, measured)
+            SVS_ARRIVE(1, SVS_SYNC_LEVEL >= 1);
+            SVS_ARRIVE(2, SVS_SYNC_LEVEL >= 1);
+            input_rowwise<CH>(ops, rawA, rawB, G.magic_hi, x);
+        } else
+#endif
         {
 #ifdef SVS_EARLY_GRAY
             uint32_t gB[16];
@@ -765,6 +820,13 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) extract_fast_ker
         for (int j = 0; j < 4; ++j) pack[warp][lane + 32 * j] = 0;
 
         P2 x[64];
+#ifndef SVS_COLUMNWISE_INPUT
+        if (CH == 3) {
+            SVS_ARRIVE(1, sync_now);
+            SVS_ARRIVE(2, sync_now);
+            input_rowwise<CH>(ops, rawA, rawB, G.magic_hi, x);
+        } else
+#endif
         {
             uint32_t gA[16], gB[16];
             raw_to_gray_arrive<CH>(rawA, gA, slot, sync_now);
