@@ -502,7 +502,8 @@ def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world
     except Exception as exc:
         return {"error": "pinned allocation failed: %r" % (exc,)}
     ctx = ctypes.c_void_p()
-    svs_b200._native.check(L.svs_ctx_create(local_rank, 3 << 30, ctypes.byref(ctx)), "svs_ctx_create")
+    staging = int(os.environ.get("SVS_BENCH_E2E_STAGING_MB", "192")) << 20
+    svs_b200._native.check(L.svs_ctx_create(local_rank, staging, ctypes.byref(ctx)), "svs_ctx_create")
 
     def one():
         rc = L.svs_embed_frames_host(ctx, h_frames.data_ptr(), CH, F, H, W, H * W * CH, W * CH,
@@ -538,7 +539,7 @@ def run_e2e(args, svs_b200, torch, dist, frames, payload, dev, local_rank, world
             # what bounds it: the host<->device link, not the kernels (both directions run concurrently)
             "pcie_h2d_gbs": F * (3 * px + nbytes + px) * steps / dt / 1e9,
             "pcie_d2h_gbs": F * (px + nbytes) * steps / dt / 1e9,
-            "api": "svs_embed_frames_host + svs_extract_frames_host (C ABI, pinned host buffers, 3-stream chunk pipeline)"}
+            "api": "svs_embed_frames_host + svs_extract_frames_host (C ABI, pinned host buffers, 3-slot chunk pipeline, %d MB of device staging)" % (staging >> 20)}
 
 
 if __name__ == "__main__":
