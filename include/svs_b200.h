@@ -170,13 +170,15 @@ int64_t svs_kernel_launch_count(void);
  * previous value.  Process-wide. */
 int svs_set_reserved_sms(int n);
 
-/* Diagnostic: selects the kernel family.  0 = automatic (default: packed-FP32 lockstep kernels
- * whenever they apply, scalar kernels otherwise), 1 = scalar one-block-per-thread kernels only,
- * 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh), 4 = packed
- * row kernels (svs_row.cuh, 8 lanes per block pair); negative
- * only queries.  Returns the previous setting.  All families produce identical results; the
- * tests use this to prove it.  Environment variable SVS_KERNEL_FAMILY sets the default. */
-int svs_debug_force_scalar(int on);
+/* Diagnostic: selects the kernel family, process-wide.  0 = automatic (default: the packed
+ * one-block-per-thread kernels of svs_block.cuh whenever they apply, the scalar kernels
+ * otherwise), 1 = scalar kernels only, 5 = packed block kernels.  A library built with
+ * -DSVS_WITH_VARIANTS (measurement builds, profiles/build_variant.sh) also knows 2 = packed
+ * lockstep (two blocks per thread), 3 = packed tile, 4 = packed row - the round-1 organisations.
+ * Returns the previous setting; a negative argument only queries; -1 is returned (and nothing
+ * changes) when this build does not contain the requested family.  All families produce
+ * identical results; the tests use this to prove it. */
+int svs_debug_kernel_family(int family_id);
 
 #ifdef __cplusplus
 }

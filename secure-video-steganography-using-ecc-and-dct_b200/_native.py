@@ -16,11 +16,24 @@ LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_quant.h"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
            os.path.join(_PKG, "csrc", "svs_tile.cuh"), os.path.join(_PKG, "csrc", "svs_row.cuh"),
+           os.path.join(_PKG, "csrc", "svs_hw.cuh"), os.path.join(_PKG, "csrc", "svs_block.cuh"),
            os.path.join(_ROOT, "include", "svs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 _lib = None
+_lib_override = None
+
+
+def use_library(path):
+    """Measurement scripts only (profiles/ab_kernels.py): load another BUILD of the same library,
+    e.g. one compiled with -DSVS_WITH_VARIANTS.  Must be called before the first lib()."""
+    global _lib_override
+    if _lib is not None:
+        raise RuntimeError("libsvs_b200.so is already loaded")
+    if not os.path.exists(path):
+        raise RuntimeError("no such library: %s" % path)
+    _lib_override = path
 
 
 class SvsError(RuntimeError):
@@ -41,12 +54,17 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    """Compile the kernels for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile the kernels for sm_100a in-tree (nvcc cross-compiles without a GPU).
+
+    `defines` / `out`: measurement builds next to the product library, e.g.
+    build(defines=["SVS_WITH_VARIANTS"], out="variants/libsvs_variants.so")."""
+    target = out or LIB_PATH
+    if not force and not defines and out is None and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"),
-                                    "-o", LIB_PATH] + SOURCES
+    os.makedirs(os.path.dirname(os.path.abspath(target)), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + \
+          ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"), "-o", target] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,7 +72,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return target
 
 
 _c = ctypes
@@ -64,7 +82,7 @@ _SIGNATURES = {
     "svs_capacity_bits": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
     "svs_bits_row_bytes": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
     "svs_kernel_launch_count": (_c.c_int64, []),
-    "svs_debug_force_scalar": (_c.c_int, [_c.c_int]),
+    "svs_debug_kernel_family": (_c.c_int, [_c.c_int]),
     "svs_set_reserved_sms": (_c.c_int, [_c.c_int]),
     "svs_extract_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
                                       _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p]),
@@ -97,8 +115,7 @@ def lib():
             raise RuntimeError(
                 "libsvs_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                 "this package has no CPU fallback." % LIB_PATH)
-        # SVS_B200_LIB: an alternative build of the SAME library (A/B measurements of kernel variants)
-        L = ctypes.CDLL(os.environ.get("SVS_B200_LIB") or LIB_PATH)
+        L = ctypes.CDLL(_lib_override or LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

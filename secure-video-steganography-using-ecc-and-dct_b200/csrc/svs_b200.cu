@@ -24,9 +24,12 @@
 #include "svs_b200.h"
 #include "svs_math.cuh"
 #include "svs_quant.h"
-#include "svs_fast.cuh"
-#include "svs_tile.cuh"
+#if defined(SVS_WITH_VARIANTS)
+#include "svs_fast.cuh"      // round-1 lockstep kernels (two blocks per thread)
+#include "svs_tile.cuh"      // measured dead ends, kept for the A/B script (profiles/build_variant.sh)
 #include "svs_row.cuh"
+#endif
+#include "svs_block.cuh"
 
 namespace {
 
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 4) extract_kernel(const ExtractArgs 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+#if defined(SVS_WITH_VARIANTS)
 // ------------------------------------------------------------------------------------------
 // Side outputs of embed for the frames the packed kernels handle: the gray reference (first
 // return value of the reference function, config_and_setup.py:111-114,172) and the per-frame
@@ -370,8 +374,8 @@ __global__ void __launch_bounds__(256) side_outputs_kernel(const SideArgs a)
             const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
             const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src) + 2);
             const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-            row::bgr8_to_gray(w, g[0], g[1]);
-            row::bgr8_to_gray(w + 6, g[2], g[3]);
+            blk::row_gray_words(w, g[0], g[1]);
+            blk::row_gray_words(w + 6, g[2], g[3]);
         }
         if (a.gray != nullptr)
             *reinterpret_cast<uint4*>(a.gray + (f * a.H + y) * (long long)(a.W16 * 16) + c * 16) = make_uint4(g[0], g[1], g[2], g[3]);
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(256) side_outputs_kernel(const SideArgs a)
         }
     }
 }
+
+#endif  // SVS_WITH_VARIANTS
 
 thread_local char g_err[256] = "";
 std::atomic<long long> g_launches{0};
@@ -475,6 +481,23 @@ void launch_extract(const ExtractArgs& a, bool words, unsigned grid, cudaStream_
 
 using svs::make_fast_quant;     // svs_quant.h
 
+// SMs the persistent grids may occupy (svs_set_reserved_sms leaves some to a concurrent collective)
+int usable_sms()
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    const int usable = sms[dev] - g_reserved_sms.load();
+    return usable < 1 ? 1 : usable;
+}
+
+#if defined(SVS_WITH_VARIANTS)
 fast::FastGeom make_fast_geometry(const Geometry& g, long long n_frames)
 {
     fast::FastGeom f;
@@ -497,37 +520,120 @@ fast::FastGeom make_fast_geometry(const Geometry& g, long long n_frames)
 // persistent grid: one CTA per SM (or fewer when there is not enough work)
 unsigned fast_grid(long long total_groups)
 {
-    static int sms[64] = {0};
+    const long long want = (total_groups + fast::kFastWarps - 1) / fast::kFastWarps;
+    const long long cap = (long long)usable_sms() * fast::kFastCtasPerSm;
+    return (unsigned)(want < cap ? want : cap);
+}
+#endif
+
+// Kernel family: 0 = automatic (block kernels when applicable, scalar otherwise), 1 = scalar only,
+// 5 = packed block kernels (svs_block.cuh: one block per thread, free-running warps).  Builds
+// with -DSVS_WITH_VARIANTS (profiles/build_variant.sh) also carry the round-1 organisations the
+// A/B measurements compare against: 2 = packed lockstep (svs_fast.cuh: two blocks per thread),
+// 3 = packed tile (svs_tile.cuh), 4 = packed row (svs_row.cuh: 8 lanes per block pair).
+std::atomic<int> g_family{0};
+
+bool family_available(int f)
+{
+#if defined(SVS_WITH_VARIANTS)
+    return f >= 0 && f <= 5;
+#else
+    return f == 0 || f == 1 || f == 5;
+#endif
+}
+
+int family() { return g_family.load(std::memory_order_relaxed); }
+
+// ---- block kernels (svs_block.cuh): one block per thread, free-running warps -----------------
+blk::Div make_div(uint32_t d)
+{
+    int l = 0;
+    while ((1ull << l) < d) ++l;
+    blk::Div r;
+    r.shift = (uint32_t)(31 + l);
+    r.mul = (uint32_t)(((1ull << (31 + l)) + d - 1) / d);        // < 2^32 because 2^l < 2 d
+    return r;
+}
+
+blk::BlkGeom make_blk_geometry(const Geometry& g, long long n_frames)
+{
+    blk::BlkGeom b;
+    b.frames = g.frames;
+    b.frame_stride = g.frame_stride;
+    b.row_stride = g.row_stride;
+    b.bw = g.bw;
+    b.bpf = g.bpf;
+    b.n = g.n;
+    b.gpf = (g.bpf + 31) / 32;
+    b.total_groups = n_frames * b.gpf;
+    b.by_gpf = make_div((uint32_t)b.gpf);
+    b.by_bw = make_div((uint32_t)g.bw);
+    b.magic_hi = 0x4B000000u;
+    b.delta32 = g.delta32;
+    return b;
+}
+
+// persistent grid: kBlkMinCtas CTAs on every usable SM (or fewer when there is not enough work)
+unsigned blk_grid(long long total_groups)
+{
+    const long long ctas = (long long)usable_sms() * blk::kBlkMinCtas;
+    const long long want = (total_groups + blk::kBlkWarps - 1) / blk::kBlkWarps;
+    return (unsigned)(want < ctas ? want : ctas);
+}
+
+// opt in to the dynamic shared memory of the cp.async slots, once per kernel instantiation and
+// device; `ready` belongs to the calling instantiation (all kernels share one pointer TYPE)
+cudaError_t blk_smem_optin(const void* kernel, int bytes, bool (&ready)[64])
+{
+    if (bytes <= 0) return cudaSuccess;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (sms[dev] == 0) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        sms[dev] = v;
-    }
-    const long long want = (total_groups + fast::kFastWarps - 1) / fast::kFastWarps;
-    int usable = sms[dev] - g_reserved_sms.load();
-    if (usable < 1) usable = 1;
-    const long long cap = (long long)usable * fast::kFastCtasPerSm;
-    return (unsigned)(want < cap ? want : cap);
+    if (ready[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) ready[dev] = true;
+    return e;
 }
 
-// Kernel family: 0 = automatic (packed lockstep kernels when applicable), 1 = scalar only,
-// 2 = packed lockstep kernels (svs_fast.cuh), 3 = packed tile kernels (svs_tile.cuh),
-// 4 = packed row kernels (svs_row.cuh: 8 lanes per block pair).
-int g_family = 0;
-
-int family()
+template <int CH, int OC, bool NFULL, bool SIDE>
+cudaError_t launch_blk_embed_one(const blk::BlkEmbedArgs& ba, cudaStream_t st)
 {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SVS_KERNEL_FAMILY");
-        env = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;
-    }
-    return g_family != 0 ? g_family : env;
+    constexpr int smem = blk::blk_smem_bytes<CH, true>();
+    static bool ready[64] = {false};
+    if (cudaError_t e = blk_smem_optin(reinterpret_cast<const void*>(blk::embed_blk_kernel<CH, OC, NFULL, SIDE>), smem, ready)) return e;
+    blk::embed_blk_kernel<CH, OC, NFULL, SIDE><<<blk_grid(ba.g.total_groups), blk::kBlkThreads, smem, st>>>(ba);
+    return cudaGetLastError();
 }
 
+template <int CH, int OC>
+cudaError_t launch_blk_embed(const blk::BlkEmbedArgs& ba, bool nfull, bool side, cudaStream_t st)
+{
+    if (nfull) return side ? launch_blk_embed_one<CH, OC, true, true>(ba, st) : launch_blk_embed_one<CH, OC, true, false>(ba, st);
+    return side ? launch_blk_embed_one<CH, OC, false, true>(ba, st) : launch_blk_embed_one<CH, OC, false, false>(ba, st);
+}
+
+template <int CH, int NP>
+cudaError_t launch_blk_extract_one(const blk::BlkExtractArgs& xa, cudaStream_t st)
+{
+    constexpr int smem = blk::blk_smem_bytes<CH, false>();
+    static bool ready[64] = {false};
+    if (cudaError_t e = blk_smem_optin(reinterpret_cast<const void*>(blk::extract_blk_kernel<CH, NP>), smem, ready)) return e;
+    blk::extract_blk_kernel<CH, NP><<<blk_grid(xa.g.total_groups), blk::kBlkThreads, smem, st>>>(xa);
+    return cudaGetLastError();
+}
+
+template <int CH>
+cudaError_t launch_blk_extract(const blk::BlkExtractArgs& xa, cudaStream_t st)
+{
+    switch ((xa.g.n + 16) / 16) {                 // coefficient row pairs that hold any of flat 1..n
+    case 1: return launch_blk_extract_one<CH, 1>(xa, st);
+    case 2: return launch_blk_extract_one<CH, 2>(xa, st);
+    case 3: return launch_blk_extract_one<CH, 3>(xa, st);
+    default: return launch_blk_extract_one<CH, 4>(xa, st);
+    }
+}
+
+#if defined(SVS_WITH_VARIANTS)
 // row kernels: free-running warps, kRowCtasPerSm CTAs on every usable SM, grid-stride over groups
 unsigned row_grid(long long total_groups)
 {
@@ -579,6 +685,7 @@ cudaError_t launch_tile_extract(const fast::FastExtractArgs& fa, cudaStream_t st
     tile::extract_tile_kernel<CH, NFULL><<<tile_grid(fa.g.total_groups), tile::kTileThreads, tile::kTileSmemBytes, st>>>(fa);
     return cudaGetLastError();
 }
+#endif  // SVS_WITH_VARIANTS
 
 }  // namespace
 
@@ -587,7 +694,7 @@ cudaError_t launch_tile_extract(const fast::FastExtractArgs& fa, cudaStream_t st
 // ==========================================================================================
 extern "C" {
 
-int svs_version(void) { return 100; }
+int svs_version(void) { return 200; }
 
 const char* svs_last_error_string(void) { return g_err; }
 
@@ -600,11 +707,11 @@ int svs_set_reserved_sms(int n)
     return prev;
 }
 
-int svs_debug_force_scalar(int on)
+int svs_debug_kernel_family(int family_id)
 {
-    const int prev = g_family;
-    if (on >= 0 && on <= 4) g_family = on;
-    return prev;
+    if (family_id < 0) return g_family.load();
+    if (!family_available(family_id)) return -1;
+    return g_family.exchange(family_id);
 }
 
 int64_t svs_capacity_bits(int height, int width, int num_ac)
@@ -644,47 +751,62 @@ static int extract_impl(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool words = aligned_to(d_bits_out, bits_frame_stride, 0, 4) && bits_frame_stride >= (cap + 31) / 32 * 4;
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const fast::FastQuant fq = make_fast_quant(delta);
-    if (family() != 1 && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
-        fast::FastExtractArgs fa;
-        fa.g = make_fast_geometry(a.g, n_frames);
-        fa.q = fq;
-        fa.bits = d_bits_out;
-        fa.bits_frame_stride = bits_frame_stride;
-        fa.n_peers = family() == 3 ? 0 : n_peers;
-        fa.multicast = multicast ? 1 : 0;
-        const bool use_row = family() == 4 && row_ok(a.g, d_frames, frame_stride, row_stride);
-        for (int e = 0; e < fa.n_peers; ++e) fa.peers[e] = peers[e];
-        const bool full = a.g.n == SVS_MAX_AC;
-        cudaError_t fe;
-        if (use_row) {
-            const unsigned rgrid = row_grid(fa.g.total_groups);
-            row::RowExtractArgs ra;
-            ra.x = fa;
-            ra.wrap_src = 8 * row_stride - (long long)a.g.bw * 8 * channels;
-            if (channels == 3) {
-                if (full) row::extract_row_kernel<3, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
-                else row::extract_row_kernel<3, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
-            } else {
-                if (full) row::extract_row_kernel<1, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
-                else row::extract_row_kernel<1, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
-            }
-            fe = cudaGetLastError();
-        } else if (family() != 3) {
-            const unsigned fgrid = fast_grid(fa.g.total_groups);
-            if (channels == 3) {
-                if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-                else fast::extract_fast_kernel<3, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            } else {
-                if (full) fast::extract_fast_kernel<1, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-                else fast::extract_fast_kernel<1, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
-            }
-            fe = cudaGetLastError();
-        } else if (channels == 3) {
-            fe = full ? launch_tile_extract<3, true>(fa, st) : launch_tile_extract<3, false>(fa, st);
-        } else {
-            fe = full ? launch_tile_extract<1, true>(fa, st) : launch_tile_extract<1, false>(fa, st);
+    const svs::FastQuant fq = make_fast_quant(delta);
+    const int fam = family();
+    if (fam != 1 && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 31) / 32) < 0x7fffffffLL) {
+        cudaError_t fe = cudaSuccess;
+        if (fam == 0 || fam == 5) {
+            blk::BlkExtractArgs xa;
+            xa.g = make_blk_geometry(a.g, n_frames);
+            xa.q = fq;
+            xa.bits = d_bits_out;
+            xa.bits_frame_stride = bits_frame_stride;
+            xa.n_peers = n_peers;
+            xa.multicast = multicast ? 1 : 0;
+            for (int e = 0; e < n_peers; ++e) xa.peers[e] = peers[e];
+            fe = channels == 3 ? launch_blk_extract<3>(xa, st) : launch_blk_extract<1>(xa, st);
         }
+#if defined(SVS_WITH_VARIANTS)
+        else {
+            fast::FastExtractArgs fa;
+            fa.g = make_fast_geometry(a.g, n_frames);
+            fa.q = fq;
+            fa.bits = d_bits_out;
+            fa.bits_frame_stride = bits_frame_stride;
+            fa.n_peers = fam == 3 ? 0 : n_peers;
+            fa.multicast = multicast ? 1 : 0;
+            for (int e = 0; e < fa.n_peers; ++e) fa.peers[e] = peers[e];
+            const bool full = a.g.n == SVS_MAX_AC;
+            if (fam == 4 && row_ok(a.g, d_frames, frame_stride, row_stride)) {
+                const unsigned rgrid = row_grid(fa.g.total_groups);
+                row::RowExtractArgs ra;
+                ra.x = fa;
+                ra.wrap_src = 8 * row_stride - (long long)a.g.bw * 8 * channels;
+                if (channels == 3) {
+                    if (full) row::extract_row_kernel<3, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                    else row::extract_row_kernel<3, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                } else {
+                    if (full) row::extract_row_kernel<1, true><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                    else row::extract_row_kernel<1, false><<<rgrid, row::kRowThreads, 0, st>>>(ra);
+                }
+                fe = cudaGetLastError();
+            } else if (fam != 3) {
+                const unsigned fgrid = fast_grid(fa.g.total_groups);
+                if (channels == 3) {
+                    if (full) fast::extract_fast_kernel<3, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                    else fast::extract_fast_kernel<3, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                } else {
+                    if (full) fast::extract_fast_kernel<1, true><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                    else fast::extract_fast_kernel<1, false><<<fgrid, fast::kFastThreads, 0, st>>>(fa);
+                }
+                fe = cudaGetLastError();
+            } else if (channels == 3) {
+                fe = full ? launch_tile_extract<3, true>(fa, st) : launch_tile_extract<3, false>(fa, st);
+            } else {
+                fe = full ? launch_tile_extract<1, true>(fa, st) : launch_tile_extract<1, false>(fa, st);
+            }
+        }
+#endif
         if (fe != cudaSuccess) return cuda_fail(fe, "svs_extract_frames launch (packed)");
     } else if (n_peers > 0) {
         return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed kernels (aligned input, padded bit rows, delta >= 1/16)");
@@ -712,12 +834,12 @@ int svs_extract_frames_scatter(const uint8_t* d_frames, int channels, int64_t n_
                                uint8_t* const* peer_bits_out, int n_peers, void* stream)
 {
     g_err[0] = 0;
-    if (n_peers < 0 || n_peers > fast::kMaxPeers) return fail(SVS_ERR_SHAPE, "n_peers must be 0..%d", fast::kMaxPeers);
+    if (n_peers < 0 || n_peers > blk::kMaxPeers) return fail(SVS_ERR_SHAPE, "n_peers must be 0..%d", blk::kMaxPeers);
     if (n_peers > 0 && peer_bits_out == nullptr) return fail(SVS_ERR_POINTER, "peer_bits_out is NULL");
     for (int e = 0; e < n_peers; ++e)
         if (peer_bits_out[e] == nullptr || !aligned_to(peer_bits_out[e], 0, 0, 4))
             return fail(SVS_ERR_ALIGNMENT, "peer buffer %d is NULL or not 4-byte aligned", e);
-    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed lockstep kernels");
+    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_scatter needs the packed kernels");
     return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
                         d_bits_out, bits_frame_stride, peer_bits_out, n_peers, false, stream);
 }
@@ -730,7 +852,7 @@ int svs_extract_frames_multicast(const uint8_t* d_frames, int channels, int64_t 
     g_err[0] = 0;
     if (mc_bits_out == nullptr || !aligned_to(mc_bits_out, 0, 0, 4))
         return fail(SVS_ERR_ALIGNMENT, "mc_bits_out is NULL or not 4-byte aligned");
-    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_multicast needs the packed lockstep / row kernels");
+    if (family() == 1 || family() == 3) return fail(SVS_ERR_ALIGNMENT, "svs_extract_frames_multicast needs the packed kernels");
     uint8_t* one[1] = {mc_bits_out};
     return extract_impl(d_frames, channels, n_frames, height, width, frame_stride, row_stride, delta, num_ac,
                         d_bits_local, bits_frame_stride, one, 1, true, stream);
@@ -783,20 +905,47 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
     const bool f64 = (double)(float)delta != delta;
     const bool al = aligned_to(d_frames, frame_stride, row_stride, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Frames the payload fills completely go to the packed-FP32 kernel; the frame in which the
+    // Frames the payload fills completely go to the packed-FP32 kernels; the frame in which the
     // payload ends and everything after it (and every special case) to the scalar kernel.
-    const fast::FastQuant fq = make_fast_quant(delta);
-    // the optional gray / SSE outputs of those frames come from a separate streaming kernel when its
-    // 16-pixel accesses apply; otherwise such a call goes to the scalar kernel altogether
+    const svs::FastQuant fq = make_fast_quant(delta);
     const bool want_side = d_gray_out != nullptr || d_sse_out != nullptr;
-    const bool side_ok = (width % 16) == 0 && aligned_to(d_frames, frame_stride, row_stride, 16) && stego_channels == 1 &&
-                         aligned_to(d_stego_out, stego_frame_stride, stego_row_stride, 16) &&
-                         (d_gray_out == nullptr || aligned_to(d_gray_out, 0, 0, 16)) && n_frames <= 65535;
-    if (family() != 1 && al && !f64 && a.active && fq.embed_ok && (!want_side || side_ok) &&
-        n_frames * ((a.g.bpf + 63) / 64) < 0x7fffffffLL) {
+    const int fam = family();
+    if (fam != 1 && al && !f64 && a.active && fq.embed_ok && n_frames * ((a.g.bpf + 31) / 32) < 0x7fffffffLL) {
         long long full = payload_total_bits / a.cap;
         if (full > n_frames) full = n_frames;
-        if (full > 0) {
+        bool done = false;
+        const bool nfull = a.g.n == SVS_MAX_AC;
+        if (full > 0 && (fam == 0 || fam == 5)) {
+            // block kernels: gray / SSE come from the bytes the thread already holds (SIDE instantiation)
+            blk::BlkEmbedArgs ba;
+            ba.g = make_blk_geometry(a.g, full);
+            ba.q = fq;
+            ba.payload = a.payload;
+            ba.payload_bit_offset = payload_bit_offset;
+            ba.payload_last_word = a.payload_last_word;
+            ba.cap = a.cap;
+            ba.stego = d_stego_out;
+            ba.stego_frame_stride = stego_frame_stride;
+            ba.stego_row_stride = stego_row_stride;
+            ba.bits_embedded = d_bits_embedded_out;
+            ba.gray = d_gray_out;
+            ba.sse = d_sse_out;
+            ba.gray_frame_stride = (long long)height * width;
+            ba.W = width;
+            cudaError_t e;
+            if (channels == 3) e = stego_channels == 1 ? launch_blk_embed<3, 1>(ba, nfull, want_side, st) : launch_blk_embed<3, 3>(ba, nfull, want_side, st);
+            else               e = stego_channels == 1 ? launch_blk_embed<1, 1>(ba, nfull, want_side, st) : launch_blk_embed<1, 3>(ba, nfull, want_side, st);
+            g_launches.fetch_add(1);
+            if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (block)");
+            done = true;
+        }
+#if defined(SVS_WITH_VARIANTS)
+        // round-1 families: their optional gray / SSE outputs come from a separate streaming kernel
+        // when its 16-pixel accesses apply; otherwise such a call goes to the scalar kernel altogether
+        const bool side_ok = (width % 16) == 0 && aligned_to(d_frames, frame_stride, row_stride, 16) && stego_channels == 1 &&
+                             aligned_to(d_stego_out, stego_frame_stride, stego_row_stride, 16) &&
+                             (d_gray_out == nullptr || aligned_to(d_gray_out, 0, 0, 16)) && n_frames <= 65535;
+        if (full > 0 && !done && (!want_side || side_ok)) {
             fast::FastEmbedArgs fa;
             fa.g = make_fast_geometry(a.g, full);
             fa.q = fq;
@@ -808,8 +957,7 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             fa.stego_frame_stride = stego_frame_stride;
             fa.stego_row_stride = stego_row_stride;
             fa.bits_embedded = d_bits_embedded_out;
-            const bool nfull = a.g.n == SVS_MAX_AC;
-            const bool use_row = family() == 4 && row_ok(a.g, d_frames, frame_stride, row_stride) &&
+            const bool use_row = fam == 4 && row_ok(a.g, d_frames, frame_stride, row_stride) &&
                                  aligned_to(d_stego_out, stego_frame_stride, stego_row_stride, 16) &&
                                  a.payload_last_word < 0x7fffffffLL;
             if (use_row) {
@@ -826,7 +974,7 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
                 if (channels == 3) { if (stego_channels == 1) SVS_LAUNCH_ROW_EMBED(3, 1); else SVS_LAUNCH_ROW_EMBED(3, 3); }
                 else               { if (stego_channels == 1) SVS_LAUNCH_ROW_EMBED(1, 1); else SVS_LAUNCH_ROW_EMBED(1, 3); }
 #undef SVS_LAUNCH_ROW_EMBED
-            } else if (family() != 3) {
+            } else if (fam != 3) {
                 const unsigned fgrid = fast_grid(fa.g.total_groups);
 #define SVS_LAUNCH_EMBED(CH, OC)                                                                         \
     do {                                                                                                 \
@@ -873,6 +1021,10 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
                 e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "svs_embed_frames launch (gray / SSE)");
             }
+            done = true;
+        }
+#endif
+        if (done) {
             if (full == n_frames) return SVS_OK;
             // the remaining frames: shift every per-frame quantity by `full`
             a.g.frames += full * frame_stride;

@@ -1,0 +1,865 @@
+// svs_block.cuh - the throughput kernels of the DCT-QIM path (included by svs_b200.cu):
+// ONE 8x8 block per thread, packed FP32 inside the block.
+//
+// Same results as the scalar kernels in svs_b200.cu, bit for bit (reference:
+// proses_frame_qim_dct, config_and_setup.py:106-174).  What the organisation is built on
+// (profiles/microbench/pipes_b200.txt: FP32 32 lanes/clk/SMSP, FADD2/FFMA2 do two lanes per
+// issue slot, the ALU pipe - LOP3/PRMT/SHF - is half rate, F2I quarter):
+//   * both halves of a 64-bit register pair belong to the SAME block: two neighbouring columns
+//     during a column pass ("column pairs", c[r*4+j] = x[r][2j], x[r][2j+1]) and two
+//     neighbouring rows during a row pass ("row pairs", q[i*8+v] = x[2i][v], x[2i+1][v]), so
+//     all four passes of embed run on FADD2/FFMA2;
+//   * the regrouping between the two layouts is a 2x2 transposition of registers.  It costs
+//     nothing on the FP32 pipe: the first butterfly stage of either transform reads each of
+//     its 8 inputs exactly once (svs_math.cuh: dct8_*_head), so that stage runs on SCALAR
+//     FADD/FMUL (one lane per instruction, same pipe cycles per lane as the packed form), reads
+//     the halves where the previous pass left them and writes where the packed tail wants them;
+//   * a thread therefore owns 32 register pairs instead of 64: half the registers of the
+//     two-blocks-per-thread organisation of round 1 (svs_lockstep.cuh), twice the resident
+//     warps, and a loop body of ~2 k instructions that fits the 32 KB instruction cache - the
+//     warps run free (no lockstep barrier) and their FP32-heavy transform phases overlap other
+//     warps' ALU-heavy quantiser / conversion phases.
+// Everything below the kernels is written on the operations of svs_hw.cuh, which also have a
+// plain C++ body: tests/host_math runs block_embed / block_extract on the CPU against the oracle.
+//
+// Only whole frames that the payload fills completely come here (k == n for every block); the
+// frame in which the payload ends, strided/unaligned inputs and non-float32 deltas are handled
+// by the scalar kernels.
+#pragma once
+
+#include "svs_hw.cuh"
+#include "svs_quant.h"
+
+namespace blk {
+
+using hw::P2;
+using hw::PackedOps;
+using svs::FastQuant;
+using svs::ScalarOps;
+using svs::Stage1;
+
+// out-of-line on the device (instruction-cache space), a plain static function for the host tests
+#if defined(__CUDACC__)
+#define SVS_RARE __host__ __device__ __noinline__
+#else
+#define SVS_RARE static
+#endif
+
+constexpr uint32_t kZone = svs::kQuantZone;        // flagged when the fraction field is < kZone
+constexpr float kRintMagic = 12582912.0f;          // 1.5 * 2^23
+
+// n / d for 0 <= n < 2^31 as one 32x32->64 multiply and one shift (host: make_div)
+struct Div {
+    uint32_t mul, shift;
+};
+SVS_HD uint32_t div_by(uint32_t n, Div d) { return (uint32_t)(((unsigned long long)n * d.mul) >> d.shift); }
+
+// what the quantiser needs, in registers
+struct QuantRegs {
+    P2 r2, ke, d2, k0;                  // embed (svs_quant.h)
+    P2 rr, kx;                          // extract
+    uint32_t emask, ebit, xmask;
+    int erot, xk;
+    float d, r, negzero;                // delta32, RN(1/delta32), -0.0f
+    float r2s, kes, kxs;                // scalar copies for the repair paths
+};
+SVS_HD QuantRegs make_quant_regs(const FastQuant& q, float delta32)
+{
+    QuantRegs c;
+    c.r2 = hw::pk(q.r2, q.r2); c.ke = hw::pk(q.ke, q.ke); c.d2 = hw::pk(q.d2, q.d2); c.k0 = hw::pk(q.k0, q.k0);
+    c.rr = hw::pk(q.r, q.r); c.kx = hw::pk(q.kx, q.kx);
+    c.emask = q.emask; c.ebit = q.ebit; c.xmask = q.xmask;
+    c.erot = q.erot; c.xk = q.xk;
+    c.d = delta32; c.r = q.r; c.negzero = q.negzero;
+    c.r2s = q.r2; c.kes = q.ke; c.kxs = q.kx;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// input: one image row of the block -> 4 column pairs of exact floats
+// ------------------------------------------------------------------------------------------
+// (2^23 + byte SEL of v) as float bits: one PRMT  [v.bSEL, 0x00, 0x00, 0x4B]
+SVS_HD uint32_t magic_byte(uint32_t v, uint32_t magic_hi, int sel) { return hw::byte_perm(v, magic_hi, 0x7540u | (uint32_t)sel); }
+
+// BGR -> gray of the 8 pixels of a row held in six words: cv2 BGR2GRAY,
+// (3735 B + 19235 G + 9798 R + 16384) >> 15 (config_and_setup.py:112), computed as two dp2a per
+// pixel with doubled weights so that the gray value is bits 16..23 of the sum s[px]; the 16-bit
+// weights are placed according to where the pixel's three bytes sit in the words (no shuffles).
+SVS_HD void bgr_row_sums(const uint32_t (&v)[6], uint32_t (&s)[8])
+{
+    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
+#pragma unroll
+    for (int px = 0; px < 8; ++px) {
+        const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
+        if (off == 0)      s[px] = hw::dp2a_hi(WR, v[wi], hw::dp2a_lo((WG << 16) | WB, v[wi], RND));
+        else if (off == 1) s[px] = hw::dp2a_hi((WR << 16) | WG, v[wi], hw::dp2a_lo(WB << 16, v[wi], RND));
+        else if (off == 2) s[px] = hw::dp2a_lo(WR, v[wi + 1], hw::dp2a_hi((WG << 16) | WB, v[wi], RND));
+        else               s[px] = hw::dp2a_lo((WR << 16) | WG, v[wi + 1], hw::dp2a_hi(WB << 16, v[wi], RND));
+    }
+}
+
+// 8 BGR pixels in six words -> their 8 gray bytes in two words
+SVS_HD void row_gray_words(const uint32_t* w, uint32_t& glo, uint32_t& ghi)
+{
+    const uint32_t v[6] = {w[0], w[1], w[2], w[3], w[4], w[5]};
+    uint32_t s[8];
+    bgr_row_sums(v, s);
+    glo = hw::byte_perm(hw::byte_perm(s[0], s[1], 0x0062u), hw::byte_perm(s[2], s[3], 0x0062u), 0x5410u);
+    ghi = hw::byte_perm(hw::byte_perm(s[4], s[5], 0x0062u), hw::byte_perm(s[6], s[7], 0x0062u), 0x5410u);
+}
+
+// CH == 1: w[0..1] are the 8 gray bytes; CH == 3: w[0..5] are the 24 BGR bytes.
+// c[0..3] = column pairs of the row; glo/ghi = the row's gray bytes (only built when WANT_GRAY).
+template <int CH, bool WANT_GRAY>
+SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& glo, uint32_t& ghi)
+{
+    const P2 unbias = hw::pk(-8388608.0f, -8388608.0f);
+    if (CH == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t a = magic_byte(w[(2 * j) >> 2], magic_hi, (2 * j) & 3);
+            const uint32_t b = magic_byte(w[(2 * j + 1) >> 2], magic_hi, (2 * j + 1) & 3);
+            c[j] = hw::add2(hw::pku(a, b), unbias);                                   // exact
+        }
+        if (WANT_GRAY) { glo = w[0]; ghi = w[1]; }
+    } else {
+        const uint32_t v[6] = {w[0], w[1], w[2], w[3], w[4], w[5]};
+        uint32_t s[8];
+        bgr_row_sums(v, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            c[j] = hw::add2(hw::pku(hw::byte_perm(s[2 * j], magic_hi, 0x7542u), hw::byte_perm(s[2 * j + 1], magic_hi, 0x7542u)), unbias);
+        if (WANT_GRAY) {
+            glo = hw::byte_perm(hw::byte_perm(s[0], s[1], 0x0062u), hw::byte_perm(s[2], s[3], 0x0062u), 0x5410u);
+            ghi = hw::byte_perm(hw::byte_perm(s[4], s[5], 0x0062u), hw::byte_perm(s[6], s[7], 0x0062u), 0x5410u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the four passes
+// ------------------------------------------------------------------------------------------
+// axis 0, forward: four packed transforms down the column pairs, in place
+SVS_HD void columns_fwd(const PackedOps& po, P2 (&c)[32])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) svs::dct8_fwd<4>(po, c + j);
+}
+
+// Only the first 2*NP coefficient rows of axis 0 (extraction with few coefficients per block:
+// the later rows are never read, config_and_setup.py:138-140); ptxas drops the unused outputs
+// and what feeds only them.
+template <int NP>
+SVS_HD void columns_fwd_pruned(const PackedOps& po, P2 (&c)[32])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        P2 X[8];
+        svs::dct8_fwd_tail(po, svs::dct8_fwd_head(po, c[j], c[4 + j], c[8 + j], c[12 + j], c[16 + j], c[20 + j], c[24 + j], c[28 + j]), X);
+#pragma unroll
+        for (int u = 0; u < 2 * NP; ++u) c[4 * u + j] = X[u];
+    }
+}
+
+// rows 2i and 2i+1 of the column-pair layout (ra, rb: 4 pairs each) through scalar stage 1 ->
+// the eight stage-1 values of both rows, packed (lo = row 2i, hi = row 2i+1)
+template <bool INVERSE>
+SVS_HD Stage1<P2> regroup_rows(const ScalarOps& so, const P2* ra, const P2* rb)
+{
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hw::unpkf(ra[j], a[2 * j], a[2 * j + 1]);
+        hw::unpkf(rb[j], b[2 * j], b[2 * j + 1]);
+    }
+    const Stage1<float> ha = INVERSE ? svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7])
+                                     : svs::dct8_fwd_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    const Stage1<float> hb = INVERSE ? svs::dct8_inv_head(so, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7])
+                                     : svs::dct8_fwd_head(so, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    Stage1<P2> h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h.v[k] = hw::pk(ha.v[k], hb.v[k]);
+    return h;
+}
+
+// axis 1, forward, rows 2i and 2i+1: X[v] = (coefficient (2i, v), coefficient (2i+1, v))
+SVS_HD void rows_fwd_pair(const PackedOps& po, const ScalarOps& so, const P2* c8, P2 (&X)[8])
+{
+    svs::dct8_fwd_tail(po, regroup_rows<false>(so, c8, c8 + 4), X);
+}
+
+// axis 0, inverse, columns 2j and 2j+1: reads the row-pair layout q, writes column pairs c[r*4+j]
+SVS_HD void columns_inv_pair(const PackedOps& po, const ScalarOps& so, const P2 (&q)[32], int j, P2 (&c)[32])
+{
+    float a[8], b[8];                         // coefficient columns 2j and 2j+1, u = 0..7
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hw::unpkf(q[8 * i + 2 * j], a[2 * i], a[2 * i + 1]);
+        hw::unpkf(q[8 * i + 2 * j + 1], b[2 * i], b[2 * i + 1]);
+    }
+    const Stage1<float> ha = svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    const Stage1<float> hb = svs::dct8_inv_head(so, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    Stage1<P2> h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h.v[k] = hw::pk(ha.v[k], hb.v[k]);
+    P2 x[8];
+    svs::dct8_inv_tail(po, h, x);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) c[4 * r + j] = x[r];
+}
+
+// axis 1, inverse, rows 2i and 2i+1: out[col] = (pixel (2i, col), pixel (2i+1, col))
+SVS_HD void rows_inv_pair(const PackedOps& po, const ScalarOps& so, const P2* c8, P2 (&out)[8])
+{
+    svs::dct8_inv_tail(po, regroup_rows<true>(so, c8, c8 + 4), out);
+}
+
+// ------------------------------------------------------------------------------------------
+// quantiser (svs_quant.h states the arithmetic and its error budget)
+// ------------------------------------------------------------------------------------------
+// IEEE-exact c / d from the correctly rounded reciprocal r = RN(1/d): two Newton corrections on
+// the quotient (the sequence __fdiv_rn runs after its own reciprocal; all operands are normal
+// here).  Checked against the FPU division in tests/test_host_logic.py.
+SVS_HD float div_exact(float c, float d, float r)
+{
+    float q = hw::fmul(c, r);
+    q = hw::ffma(hw::ffma(-q, d, c), r, q);
+    return hw::ffma(hw::ffma(-q, d, c), r, q);
+}
+
+// Coefficients (0,4), (4,0) and (4,4) of a block of integer pixels are exact multiples of 1/8
+// (their basis is +-1/8), so c / delta lands EXACTLY on a rounding tie in one block out of
+// 8 delta - far too often for the speculate-and-repair quantiser.  They are always quantised
+// with the IEEE-exact quotient, on scalar registers (all three sit in the low half of their
+// row pair), rint() through the 1.5 * 2^23 constant: round-half-even, the parity is the lowest
+// mantissa bit (two's complement for negative quotients).
+SVS_HD bool tie_prone(int flat) { return flat == 4 || flat == 32 || flat == 36; }
+
+SVS_HD float exact_embed(float c, uint32_t bit, const QuantRegs& Q)         // config_and_setup.py:148-156
+{
+    const float m = hw::fadd(div_exact(c, Q.d, Q.r), kRintMagic);
+    const float adj = hw::i2f((int)bit - (int)(hw::f2u(m) & 1u));
+    return hw::fmul(hw::fadd(hw::fsub(m, kRintMagic), adj), Q.d);
+}
+SVS_HD uint32_t exact_parity(float c, const QuantRegs& Q)                   // config_and_setup.py:160-161
+{
+    return hw::f2u(hw::fadd(div_exact(c, Q.d, Q.r), kRintMagic)) & 1u;
+}
+
+// payload bit `idx` (0 = first) of the block's 64-bit window (w0 = bits 0..31, MSB first)
+SVS_HD uint32_t window_bit(uint32_t w0, uint32_t w1, int idx) { return ((idx < 32 ? w0 : w1) >> (31 - (idx & 31))) & 1u; }
+
+// Rare path, deliberately out of line and looped so that it costs almost no instruction-cache
+// space.  `orig` holds the 8 coefficient pairs of rows 2i / 2i+1 before quantisation, `res`
+// the results of the division-free quantiser; every coefficient whose fraction was too close
+// to a rounding boundary is recomputed as the scalar kernels do (IEEE division, round-half-
+// even, float32 product) and patched into `res`.
+SVS_RARE void fix_pair_embed(const P2* orig, P2* res, int i, int n, float d, float r, float r2, float ke, uint32_t emask,
+                    uint32_t w0, uint32_t w1)
+{
+#pragma unroll 1
+    for (int v = 0; v < 8; ++v) {
+        float c[2], o[2];
+        hw::unpkf(orig[v], c[0], c[1]);
+        hw::unpkf(res[v], o[0], o[1]);
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+            const int idx = 16 * i + 8 * l + v - 1;
+            if (idx < 0 || idx >= n) continue;
+            if ((hw::f2u(hw::ffma(c[l], r2, ke)) & emask) < kZone) {
+                const int q = hw::f2i_rn(div_exact(c[l], d, r));
+                o[l] = hw::fmul(hw::i2f(q - (q & 1) + (int)window_bit(w0, w1, idx)), d);
+            }
+        }
+        res[v] = hw::pk(o[0], o[1]);
+    }
+}
+
+// Same for extraction: `rows` = (row 2i byte | row 2i+1 byte << 16), coefficient v at bit 7-v;
+// flagged coefficients get their parity from the exact quotient.
+SVS_RARE uint32_t fix_pair_extract(const P2* in, uint32_t rows, int i, int n, float d, float r, float kx, uint32_t xmask)
+{
+#pragma unroll 1
+    for (int v = 0; v < 8; ++v) {
+        float c[2];
+        hw::unpkf(in[v], c[0], c[1]);
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+            const int idx = 16 * i + 8 * l + v - 1;
+            if (idx < 0 || idx >= n) continue;
+            if ((hw::f2u(hw::ffma(c[l], r, kx)) & xmask) < kZone) {
+                const uint32_t par = (uint32_t)hw::f2i_rn(div_exact(c[l], d, r)) & 1u;
+                const int at = 16 * l + 7 - v;
+                rows = (rows & ~(1u << at)) | (par << at);
+            }
+        }
+    }
+    return rows;
+}
+
+// Embed into rows 2i, 2i+1 (X in, quantised coefficients out, in place).  Payload bit idx =
+// 8u + v - 1 goes to coefficient (u, v): row-major flat index 1..n (config_and_setup.py:138-141).
+// p0/p1 are the window words pre-rotated so that bit idx sits `idx` places below position
+// erot: bringing it there is a rotate by the compile-time constant idx.
+template <bool NFULL>
+SVS_HD void quant_embed_pair(int i, P2 (&X)[8], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t p0, uint32_t p1)
+{
+    uint32_t worst = 0xffffffffu;
+    P2 nx[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int il = 16 * i + v - 1, ih = il + 8;             // payload bit numbers of the two halves
+        const bool tie = tie_prone(16 * i + v);                 // only ever the low half
+        const bool al = il >= 0 && (NFULL || il < n), ah = NFULL || ih < n;
+        const P2 y = hw::fma2(X[v], Q.r2, Q.ke);
+        uint32_t ya, yb;
+        hw::unpk(y, ya, yb);
+        if (al && !tie) worst = hw::umin(worst, ya & Q.emask);
+        if (ah) worst = hw::umin(worst, yb & Q.emask);
+        const int jl = il < 0 ? 0 : il;
+        const uint32_t ta = hw::funnel_l(jl < 32 ? p0 : p1, jl < 32 ? p0 : p1, jl & 31) & Q.ebit;
+        const uint32_t tb = hw::funnel_l(ih < 32 ? p0 : p1, ih < 32 ? p0 : p1, ih & 31) & Q.ebit;
+        // M + floor() + bit/2, then (2e + bit) * delta in one rounding
+        const P2 z = hw::fma2(hw::pku((ya & ~Q.emask) | ta, (yb & ~Q.emask) | tb), Q.d2, Q.k0);
+        if (NFULL && !tie && il >= 0) {
+            nx[v] = z;
+        } else {
+            float lo = hw::lo_of(z), hi = hw::hi_of(z);
+            if (tie) lo = exact_embed(hw::lo_of(X[v]), window_bit(w0, w1, jl), Q);
+            if (!al) lo = hw::lo_of(X[v]);
+            if (!ah) hi = hw::hi_of(X[v]);
+            nx[v] = hw::pk(lo, hi);
+        }
+    }
+    if (worst < kZone) {                                         // rare: a fraction too close to call
+        // (copies made HERE: arrays whose address escapes live in local memory, and X / nx must not)
+        P2 orig[8], res[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) { orig[v] = X[v]; res[v] = nx[v]; }
+        fix_pair_embed(orig, res, i, NFULL ? 63 : n, Q.d, Q.r, Q.r2s, Q.kes, Q.emask, w0, w1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) nx[v] = res[v];
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) X[v] = nx[v];
+}
+
+// Parities of rows 2i, 2i+1: returns (row 2i byte | row 2i+1 byte << 16), coefficient v at bit 7-v.
+SVS_HD uint32_t quant_extract_pair(int i, const P2 (&X)[8], const QuantRegs& Q, int n)
+{
+    uint32_t worst = 0xffffffffu, rl = 0, rh = 0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const bool tie = tie_prone(16 * i + v);
+        const bool dc = i == 0 && v == 0;
+        const P2 y = hw::fma2(X[v], Q.rr, Q.kx);
+        uint32_t ya, yb;
+        hw::unpk(y, ya, yb);
+        const int rot = (7 - v - Q.xk) & 31;                     // parity (bit xk) -> bit 7-v
+        if (tie) {
+            rl |= exact_parity(hw::lo_of(X[v]), Q) << (7 - v);
+        } else if (!dc) {
+            worst = hw::umin(worst, ya & Q.xmask);
+            rl |= hw::funnel_l(ya, ya, rot) & (0x80u >> v);
+        }
+        worst = hw::umin(worst, yb & Q.xmask);
+        rh |= hw::funnel_l(yb, yb, rot) & (0x80u >> v);
+    }
+    uint32_t rows = rl | (rh << 16);
+    if (worst < kZone) {
+        P2 in[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) in[v] = X[v];
+        rows = fix_pair_extract(in, rows, i, n, Q.d, Q.r, Q.kxs, Q.xmask);
+    }
+    return rows;
+}
+
+// byte of coefficient row u (bit 7-v = coefficient v) -> stream bits 8u-1 .. 8u+6 of the block's
+// 64-bit string (hi:lo), stream bit s at bit 63-s; the DC position falls off the top
+SVS_HD void place_row(int u, uint32_t byte, uint32_t& hi, uint32_t& lo)
+{
+    if (u < 4)       hi |= byte << (25 - 8 * u);
+    else if (u == 4) { hi |= byte >> 7; lo |= byte << 25; }
+    else             lo |= byte << (57 - 8 * u);
+}
+
+// ------------------------------------------------------------------------------------------
+// whole blocks (shared by the kernels and by tests/host_math)
+// ------------------------------------------------------------------------------------------
+// rows: 8 x (CH == 3 ? 6 : 2) words of the block's image rows -> column pairs c (and the
+// gray bytes, row r at [2r], [2r+1], when WANT_GRAY)
+template <int CH, bool WANT_GRAY>
+SVS_HD void block_input(const uint32_t* rows, uint32_t magic_hi, P2 (&c)[32], uint32_t* gray)
+{
+    constexpr int P = CH == 3 ? 6 : 2;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint32_t glo = 0, ghi = 0;
+        row_to_pairs<CH, WANT_GRAY>(rows + r * P, magic_hi, c + 4 * r, glo, ghi);
+        if (WANT_GRAY) { gray[2 * r] = glo; gray[2 * r + 1] = ghi; }
+    }
+}
+
+// c: the block as column pairs (destroyed).  stego: 16 words (row r at [2r], [2r+1]).  Every
+// block coming here takes all n bits.
+template <bool NFULL>
+SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t* stego)
+{
+    PackedOps po;
+    po.negzero = hw::pk(Q.negzero, Q.negzero);
+    const ScalarOps so;
+    columns_fwd(po, c);
+    const int pre = (Q.erot - 31) & 31;
+    const uint32_t p0 = hw::funnel_l(w0, w0, pre), p1 = hw::funnel_l(w1, w1, pre);
+    P2 q[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        P2 X[8];
+        rows_fwd_pair(po, so, c + 8 * i, X);
+        if (NFULL || 16 * i - 1 < n) quant_embed_pair<NFULL>(i, X, Q, n, w0, w1, p0, p1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) q[8 * i + v] = X[v];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) columns_inv_pair(po, so, q, j, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        P2 o[8];
+        rows_inv_pair(po, so, c + 8 * i, o);
+        uint32_t ba[8], bb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            ba[k] = hw::to_u8(hw::lo_of(o[k]));                 // clip then truncate (config_and_setup.py:171)
+            bb[k] = hw::to_u8(hw::hi_of(o[k]));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            stego[4 * i + h] = hw::byte_perm(hw::byte_perm(ba[4 * h], ba[4 * h + 1], 0x0040u), hw::byte_perm(ba[4 * h + 2], ba[4 * h + 3], 0x0040u), 0x5410u);
+            stego[4 * i + 2 + h] = hw::byte_perm(hw::byte_perm(bb[4 * h], bb[4 * h + 1], 0x0040u), hw::byte_perm(bb[4 * h + 2], bb[4 * h + 3], 0x0040u), 0x5410u);
+        }
+    }
+}
+
+template <int CH, bool NFULL, bool WANT_GRAY>
+SVS_HD void block_embed(const uint32_t* rows, uint32_t magic_hi, const QuantRegs& Q, int n, uint32_t w0, uint32_t w1,
+                        uint32_t* stego, uint32_t* gray)
+{
+    P2 c[32];
+    block_input<CH, WANT_GRAY>(rows, magic_hi, c, gray);
+    block_embed_pairs<NFULL>(c, Q, n, w0, w1, stego);
+}
+
+// NP = number of coefficient row pairs that hold any of the n coefficients: ceil((n + 1) / 16).
+// c: the block as column pairs (destroyed).  Returns the block's n parity bits as a 64-bit
+// string (hi:lo), stream bit s at bit 63-s.
+template <int NP>
+SVS_HD void block_extract_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t& hi, uint32_t& lo)
+{
+    PackedOps po;
+    po.negzero = hw::pk(Q.negzero, Q.negzero);
+    const ScalarOps so;
+    if (NP == 4) columns_fwd(po, c);
+    else columns_fwd_pruned<NP>(po, c);
+    hi = 0;
+    lo = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        P2 X[8];
+        rows_fwd_pair(po, so, c + 8 * i, X);
+        const uint32_t rows2 = quant_extract_pair(i, X, Q, n);
+        place_row(2 * i, rows2 & 0xffu, hi, lo);
+        place_row(2 * i + 1, rows2 >> 16, hi, lo);
+    }
+    // bits n.. of the string are not part of the stream (config_and_setup.py:138-140)
+    if (n < 32) { hi &= ~(0xffffffffu >> n); lo = 0; }
+    else if (n < 64) lo &= n == 32 ? 0u : ~(0xffffffffu >> (n - 32));
+}
+
+template <int CH, int NP>
+SVS_HD void block_extract(const uint32_t* rows, uint32_t magic_hi, const QuantRegs& Q, int n, uint32_t& hi, uint32_t& lo)
+{
+    P2 c[32];
+    block_input<CH, false>(rows, magic_hi, c, nullptr);
+    block_extract_pairs<NP>(c, Q, n, hi, lo);
+}
+
+#if defined(__CUDACC__)
+// ==========================================================================================
+// kernels
+// ==========================================================================================
+#ifndef SVS_BLK_THREADS
+#define SVS_BLK_THREADS 256
+#endif
+#ifndef SVS_BLK_MIN_CTAS
+#define SVS_BLK_MIN_CTAS 2
+#endif
+// How the rows of a group reach the registers:
+//   0  LDG at the top of the group (the warp waits for HBM once per group);
+//   1  the same, plus prefetch.global.L2 of the NEXT group's rows;
+//   2  the next group's rows are requested as soon as the current ones have been converted to
+//      floats: with cp.async into a thread-private shared-memory slot (BGR input: 48 words;
+//      gray input of embed: 16), or straight into the 16 registers that just became free (gray
+//      input of extract) - either way they arrive while the current group is being transformed
+//      (default).
+#ifndef SVS_BLK_STAGE
+#define SVS_BLK_STAGE 2
+#endif
+constexpr int kBlkThreads = SVS_BLK_THREADS;
+constexpr int kBlkMinCtas = SVS_BLK_MIN_CTAS;
+constexpr int kBlkWarps = kBlkThreads / 32;
+constexpr int kBlkStage = SVS_BLK_STAGE;
+constexpr int kMaxPeers = 15;
+
+// Which instantiations stage through shared memory (the rest of mode 2 reuse the row registers):
+// BGR input always (48 words), gray input only in embed (its 16 row words + the payload words
+// do not fit next to the 64 coefficient registers).
+template <int CH, bool EMBED>
+constexpr bool blk_uses_smem() { return kBlkStage == 2 && (CH == 3 || EMBED); }
+// dynamic shared memory of a kernel instantiation: the cp.async slots, 8 bytes x rows x words x threads
+template <int CH, bool EMBED>
+constexpr int blk_smem_bytes() { return blk_uses_smem<CH, EMBED>() ? 8 * (CH == 3 ? 3 : 1) * 8 * kBlkThreads : 0; }
+
+// A warp owns 32 consecutive blocks of a frame in raster order ("group"): BGR rows arrive as
+// three 8-byte accesses per lane over one 768-byte contiguous span, stego rows leave as
+// 256-byte STG.64 runs, and the 32 n extracted bits form n 4-byte aligned words.
+struct BlkGeom {
+    const uint8_t* frames;
+    long long frame_stride, row_stride;
+    int bw, bpf, n;
+    int gpf;                                      // groups per frame = ceil(bpf / 32)
+    long long total_groups;                       // n_frames * gpf, < 2^31
+    Div by_gpf, by_bw;
+    uint32_t magic_hi;                            // 0x4B000000, opaque so that it stays in a register
+    float delta32;
+};
+
+struct BlkEmbedArgs {
+    BlkGeom g;
+    FastQuant q;
+    const uint32_t* payload;
+    long long payload_bit_offset, payload_last_word, cap;
+    uint8_t* stego;
+    long long stego_frame_stride, stego_row_stride;
+    int64_t* bits_embedded;
+    uint8_t* gray;                                // nullable; contiguous H x W frames   (SIDE kernels only)
+    unsigned long long* sse;                      // nullable; per-frame sum of squares  (SIDE kernels only)
+    long long gray_frame_stride;                  // H * W
+    int W;
+};
+
+struct BlkExtractArgs {
+    BlkGeom g;
+    FastQuant q;
+    uint8_t* bits;
+    long long bits_frame_stride;
+    // fused all-gather: the same rows are also stored to these (peer-mapped, NVLink) buffers;
+    // multicast != 0: peers[0] is ONE NVSwitch multicast (multimem) address that reaches every
+    // rank including this one, and `bits` is not written separately
+    uint8_t* peers[kMaxPeers];
+    int n_peers;
+    int multicast;
+};
+
+struct Where {
+    int f, base, by, bx;
+    bool ok;
+};
+__device__ __forceinline__ Where locate(const BlkGeom& G, long long g, int lane)
+{
+    Where w;
+    const uint32_t gi = (uint32_t)g;
+    w.f = (int)div_by(gi, G.by_gpf);
+    w.base = (int)(gi - (uint32_t)w.f * (uint32_t)G.gpf) * 32;
+    w.ok = w.base + lane < G.bpf;
+    const int b = min(w.base + lane, G.bpf - 1);
+    w.by = (int)div_by((uint32_t)b, G.by_bw);
+    w.bx = b - w.by * G.bw;
+    return w;
+}
+
+template <int CH>
+__device__ __forceinline__ const uint8_t* block_src(const BlkGeom& G, const Where& w)
+{
+    return G.frames + w.f * G.frame_stride + (long long)(w.by * 8) * G.row_stride + w.bx * (8 * CH);
+}
+
+template <int CH>
+__device__ __forceinline__ void load_rows(const BlkGeom& G, const Where& w, uint32_t* rows)
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+    const uint8_t* p = block_src<CH>(G, w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + j);
+            rows[(r * P + j) * 2] = v.x;
+            rows[(r * P + j) * 2 + 1] = v.y;
+        }
+        p += G.row_stride;
+    }
+}
+
+// every 32-byte sector of the warp's 8 row spans holds the first byte of some lane's part
+template <int CH>
+__device__ __forceinline__ void prefetch_rows_l2(const BlkGeom& G, const Where& w)
+{
+    const uint8_t* p = block_src<CH>(G, w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        p += G.row_stride;
+    }
+}
+
+// cp.async staging: slot (r, j) of thread t is 8 bytes at ((r*P + j) * kBlkThreads + t) * 8 of the
+// dynamic shared memory - thread-private, conflict-free, no barrier needed.
+template <int CH>
+__device__ __forceinline__ void stage_request(const BlkGeom& G, const Where& w, uint32_t slot0)
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+    const uint8_t* p = block_src<CH>(G, w);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot0 + (uint32_t)((r * P + j) * kBlkThreads * 8)), "l"(p + 8 * j) : "memory");
+        p += G.row_stride;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int CH>
+__device__ __forceinline__ void stage_fetch(uint32_t slot0, uint32_t* rows)
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 8 * P; ++k)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rows[2 * k]), "=r"(rows[2 * k + 1]) : "r"(slot0 + (uint32_t)(k * kBlkThreads * 8)) : "memory");
+}
+
+// the three payload words that hold the block's 64-bit window, as loaded (big-endian bit order inside bytes)
+struct PayWords {
+    uint32_t a, b, c, s;
+};
+__device__ __forceinline__ PayWords payload_request(const uint32_t* __restrict__ words, long long last_word, long long pos)
+{
+    PayWords p;
+    const long long wi = pos >> 5;
+    p.s = (uint32_t)(pos & 31);
+    p.a = wi <= last_word ? __ldg(words + wi) : 0u;
+    p.b = wi + 1 <= last_word ? __ldg(words + wi + 1) : 0u;
+    p.c = wi + 2 <= last_word ? __ldg(words + wi + 2) : 0u;
+    return p;
+}
+__device__ __forceinline__ void payload_window(const PayWords& p, uint32_t& w0, uint32_t& w1)
+{
+    const uint32_t a = hw::bswap(p.a), b = hw::bswap(p.b), c = hw::bswap(p.c);
+    w0 = __funnelshift_l(b, a, p.s);
+    w1 = __funnelshift_l(c, b, p.s);
+}
+
+__device__ __forceinline__ void stg64(uint8_t* p, uint32_t lo, uint32_t hi)
+{
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
+
+template <int OUT_CH>
+__device__ __forceinline__ void store_row(uint8_t* dst, uint32_t lo4, uint32_t hi4)
+{
+    if (OUT_CH == 1) {
+        stg64(dst, lo4, hi4);
+    } else {            // gray replicated to B,G,R (cv2.cvtColor GRAY2BGR, embed_process.py:126)
+        stg64(dst, __byte_perm(lo4, 0, 0x1000), __byte_perm(lo4, 0, 0x2211));
+        stg64(dst + 8, __byte_perm(lo4, 0, 0x3332), __byte_perm(hi4, 0, 0x1000));
+        stg64(dst + 16, __byte_perm(hi4, 0, 0x2211), __byte_perm(hi4, 0, 0x3332));
+    }
+}
+
+extern __shared__ __align__(16) unsigned char blk_dyn_smem[];
+
+// SIDE: also the gray reference (first return value of the reference function,
+// config_and_setup.py:111-114,172) and / or the per-frame sum of squared differences gray vs
+// stego (what cv2.PSNR needs, embed_process.py:204-206), from the bytes the thread already holds.
+template <int CH, int OUT_CH, bool NFULL, bool SIDE>
+__global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(const BlkEmbedArgs a)
+{
+    const BlkGeom& G = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = NFULL ? 63 : G.n;
+    const QuantRegs Q = make_quant_regs(a.q, G.delta32);
+    const long long gstep = (long long)gridDim.x * kBlkWarps;
+    long long g = (long long)blockIdx.x * kBlkWarps + warp;
+    if (g >= G.total_groups) return;
+    constexpr bool kStaged = kBlkStage == 2;
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(blk_dyn_smem) + threadIdx.x * 8u;
+    (void)slot0;
+
+    Where w = locate(G, g, lane);
+    uint32_t rows[CH == 3 ? 48 : 16];
+    PayWords pw;
+    auto payload_pos = [&](const Where& x) {
+        return a.payload_bit_offset + x.f * a.cap + (long long)min(x.base + lane, G.bpf - 1) * n;
+    };
+    if (kStaged) {
+        stage_request<CH>(G, w, slot0);
+        pw = payload_request(a.payload, a.payload_last_word, payload_pos(w));
+    }
+    for (;;) {
+        if (!kStaged) {
+            load_rows<CH>(G, w, rows);
+            pw = payload_request(a.payload, a.payload_last_word, payload_pos(w));
+        } else {
+            stage_fetch<CH>(slot0, rows);
+        }
+        if (w.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[w.f] = a.cap;
+        P2 c[32];
+        uint32_t stego[16], gray[16];
+        block_input<CH, SIDE>(rows, G.magic_hi, c, gray);
+        uint32_t w0, w1;
+        payload_window(pw, w0, w1);
+
+        // the next group of this warp: its rows (and payload words) are requested now
+        const long long gn = g + gstep;
+        const bool more = gn < G.total_groups;
+        Where wn = w;
+        if (more) {
+            wn = locate(G, gn, lane);
+            if (kStaged) {
+                stage_request<CH>(G, wn, slot0);
+                pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
+            } else if (kBlkStage == 1) {
+                prefetch_rows_l2<CH>(G, wn);
+            }
+        }
+
+        block_embed_pairs<NFULL>(c, Q, n, w0, w1, stego);
+        if (w.ok) {
+            uint8_t* dst = a.stego + w.f * a.stego_frame_stride + (long long)(w.by * 8) * a.stego_row_stride + w.bx * (8 * OUT_CH);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                store_row<OUT_CH>(dst, stego[2 * r], stego[2 * r + 1]);
+                dst += a.stego_row_stride;
+            }
+        }
+        if (SIDE) {
+            if (a.gray != nullptr && w.ok) {
+                uint8_t* gd = a.gray + w.f * a.gray_frame_stride + (long long)(w.by * 8) * a.W + w.bx * 8;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) stg64(gd + (long long)r * a.W, gray[2 * r], gray[2 * r + 1]);
+            }
+            if (a.sse != nullptr) {
+                uint32_t sq = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t d = hw::absdiff4(gray[k], stego[k]);
+                    sq = hw::dp4a(d, d, sq);                                 // <= 64 * 255^2 per block
+                }
+                if (!w.ok) sq = 0;
+                sq = __reduce_add_sync(0xffffffffu, sq);
+                if (lane == 0 && sq != 0) atomicAdd(a.sse + w.f, (unsigned long long)sq);
+            }
+        }
+        if (!more) break;
+        g = gn;
+        w = wn;
+    }
+}
+
+// Stores the (up to 64) packed words of one group: to this rank's buffer and to every peer
+// (plain stores into peer-mapped memory), or once to the multicast address.
+__device__ __forceinline__ void store_group_words(const BlkExtractArgs& a, long long row_off, int lane, int nwords,
+                                                  const uint32_t (&wv)[2])
+{
+    if (a.multicast) {
+        uint32_t* m32 = reinterpret_cast<uint32_t*>(a.peers[0] + row_off);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (lane + 32 * j < nwords)
+                asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(m32 + lane + 32 * j), "r"(wv[j]) : "memory");
+        return;
+    }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(a.bits + row_off);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        if (lane + 32 * j < nwords) o32[lane + 32 * j] = wv[j];
+    for (int e = 0; e < a.n_peers; ++e) {
+        uint32_t* p32 = reinterpret_cast<uint32_t*>(a.peers[e] + row_off);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (lane + 32 * j < nwords) p32[lane + 32 * j] = wv[j];
+    }
+}
+
+template <int CH, int NP>
+__global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(const BlkExtractArgs a)
+{
+    __shared__ uint32_t pack[kBlkWarps][64];
+    const BlkGeom& G = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = NP == 4 ? (G.n >= 63 ? 63 : G.n) : G.n;
+    const QuantRegs Q = make_quant_regs(a.q, G.delta32);
+    const long long gstep = (long long)gridDim.x * kBlkWarps;
+    long long g = (long long)blockIdx.x * kBlkWarps + warp;
+    if (g >= G.total_groups) return;
+    constexpr bool kStaged = kBlkStage == 2;
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(blk_dyn_smem) + threadIdx.x * 8u;
+    (void)slot0;
+
+    Where w = locate(G, g, lane);
+    uint32_t rows[CH == 3 ? 48 : 16];
+    if (kStaged) {
+        if (CH == 3) stage_request<CH>(G, w, slot0);
+        else load_rows<CH>(G, w, rows);
+    }
+    for (;;) {
+        if (!kStaged) load_rows<CH>(G, w, rows);
+        else if (CH == 3) stage_fetch<CH>(slot0, rows);
+        pack[warp][lane] = 0;
+        pack[warp][lane + 32] = 0;
+        P2 c[32];
+        block_input<CH, false>(rows, G.magic_hi, c, nullptr);
+
+        const long long gn = g + gstep;
+        const bool more = gn < G.total_groups;
+        Where wn = w;
+        if (more) {
+            wn = locate(G, gn, lane);
+            if (kStaged) {
+                if (CH == 3) stage_request<CH>(G, wn, slot0);
+                else load_rows<CH>(G, wn, rows);
+            } else if (kBlkStage == 1) {
+                prefetch_rows_l2<CH>(G, wn);
+            }
+        }
+
+        uint32_t hi, lo;
+        block_extract_pairs<NP>(c, Q, n, hi, lo);
+        if (!w.ok) { hi = 0; lo = 0; }
+        __syncwarp();
+        {   // place the n-bit string at bit offset lane*n of the warp's run of 32 n bits = n words
+            uint32_t* p = pack[warp];
+            const uint32_t o = (uint32_t)lane * (uint32_t)n, i0 = o >> 5, sh = o & 31;
+            const uint32_t q0 = hi >> sh, q1 = __funnelshift_r(lo, hi, sh), q2 = __funnelshift_r(0u, lo, sh);
+            if (q0) atomicOr(p + i0, q0);
+            if (q1) atomicOr(p + i0 + 1, q1);
+            if (q2) atomicOr(p + i0 + 2, q2);
+        }
+        __syncwarp();
+        const int nblk = min(32, G.bpf - w.base);
+        const int nwords = (nblk * n + 31) >> 5;
+        const long long row_off = w.f * a.bits_frame_stride + (long long)(w.base >> 5) * (4 * n);
+        uint32_t wv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) wv[j] = hw::bswap(pack[warp][lane + 32 * j]);
+        store_group_words(a, row_off, lane, nwords, wv);
+        __syncwarp();
+        if (!more) break;
+        g = gn;
+        w = wn;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace blk

@@ -51,17 +51,40 @@ struct ScalarOps {
 #endif
 };
 
-// Forward DCT-II (norm='ortho'): x[0], x[S], ..., x[7S] in place.
-template <int S, class A>
-SVS_HD void dct8_fwd(const A& o, typename A::T* x)
+// The first butterfly stage of either transform reads every input exactly once (8 operations);
+// everything after it only combines the 8 stage-1 values.  They are split so that the packed
+// one-block-per-thread kernels (svs_block.cuh) can run stage 1 on SCALAR registers - which
+// regroups the 8x8 block from column pairs to row pairs for free - and the tail packed.
+// dct8_fwd / dct8_inv below are head + tail, so every user executes the same 54 operations.
+template <class T>
+struct Stage1 {
+    T v[8];
+};
+
+// forward head: s07, a1, a2, a3, a4, a5, a6, d07   (A.1 steps 1-3, the input butterflies)
+template <class A>
+SVS_HD Stage1<typename A::T> dct8_fwd_head(const A& o, typename A::T x0, typename A::T x1, typename A::T x2,
+                                           typename A::T x3, typename A::T x4, typename A::T x5,
+                                           typename A::T x6, typename A::T x7)
+{
+    Stage1<typename A::T> h;
+    h.v[0] = o.add(x0, x7);
+    h.v[1] = o.add(x1, x2);
+    h.v[2] = o.sub(x2, x1);
+    h.v[3] = o.add(x3, x4);
+    h.v[4] = o.sub(x4, x3);
+    h.v[5] = o.add(x5, x6);
+    h.v[6] = o.sub(x6, x5);
+    h.v[7] = o.sub(x0, x7);
+    return h;
+}
+
+// forward tail: the remaining 46 operations; X[0..7] out
+template <class A>
+SVS_HD void dct8_fwd_tail(const A& o, const Stage1<typename A::T>& h, typename A::T (&X)[8])
 {
     typedef typename A::T T;
-    const T x0 = x[0], x1 = x[S], x2 = x[2 * S], x3 = x[3 * S];
-    const T x4 = x[4 * S], x5 = x[5 * S], x6 = x[6 * S], x7 = x[7 * S];
-    const T a1 = o.add(x1, x2), a2 = o.sub(x2, x1);
-    const T a3 = o.add(x3, x4), a4 = o.sub(x4, x3);
-    const T a5 = o.add(x5, x6), a6 = o.sub(x6, x5);
-    const T s07 = o.add(x0, x7), d07 = o.sub(x0, x7);
+    const T s07 = h.v[0], a1 = h.v[1], a2 = h.v[2], a3 = h.v[3], a4 = h.v[4], a5 = h.v[5], a6 = h.v[6], d07 = h.v[7];
     const T h1 = o.add(a1, a5), tr = o.sub(a1, a5);
     const T ti = o.add(a2, a6), h2 = o.sub(a2, a6);
     const T wti = o.mulc(ti, SVS_W), wtr = o.mulc(tr, SVS_W);
@@ -75,37 +98,62 @@ SVS_HD void dct8_fwd(const A& o, typename A::T* x)
     T t1, t2;
     t1 = o.add(o.mulc(e7, SVS_Q1), o.mulc(e1, SVS_Q7));
     t2 = o.sub(o.mulc(e1, SVS_Q1), o.mulc(e7, SVS_Q7));
-    x[S] = o.add(t1, t2);
-    x[7 * S] = o.sub(t1, t2);
+    X[1] = o.add(t1, t2);
+    X[7] = o.sub(t1, t2);
     t1 = o.add(o.mulc(e6, SVS_Q2), o.mulc(e2, SVS_Q6));
     t2 = o.sub(o.mulc(e2, SVS_Q2), o.mulc(e6, SVS_Q6));
-    x[2 * S] = o.add(t1, t2);
-    x[6 * S] = o.sub(t1, t2);
+    X[2] = o.add(t1, t2);
+    X[6] = o.sub(t1, t2);
     t1 = o.add(o.mulc(e5, SVS_Q3), o.mulc(e3, SVS_Q5));
     t2 = o.sub(o.mulc(e3, SVS_Q3), o.mulc(e5, SVS_Q5));
-    x[3 * S] = o.add(t1, t2);
-    x[5 * S] = o.sub(t1, t2);
-    x[4 * S] = o.mulc(e4, SVS_HW);
-    x[0] = o.mulc(e0, SVS_HW);
+    X[3] = o.add(t1, t2);
+    X[5] = o.sub(t1, t2);
+    X[4] = o.mulc(e4, SVS_HW);
+    X[0] = o.mulc(e0, SVS_HW);
 }
 
-// Inverse (DCT-III, scipy idct type=2 norm='ortho'): x[0], x[S], ..., x[7S] in place.
+// Forward DCT-II (norm='ortho'): x[0], x[S], ..., x[7S] in place.
 template <int S, class A>
-SVS_HD void dct8_inv(const A& o, typename A::T* x)
+SVS_HD void dct8_fwd(const A& o, typename A::T* x)
+{
+    typename A::T X[8];
+    dct8_fwd_tail(o, dct8_fwd_head(o, x[0], x[S], x[2 * S], x[3 * S], x[4 * S], x[5 * S], x[6 * S], x[7 * S]), X);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k * S] = X[k];
+}
+
+// inverse head: c0, c4, X1+X7, X1-X7, X2+X6, X2-X6, X3+X5, X3-X5   (A.2 steps 1-3, first half)
+template <class A>
+SVS_HD Stage1<typename A::T> dct8_inv_head(const A& o, typename A::T X0, typename A::T X1, typename A::T X2,
+                                           typename A::T X3, typename A::T X4, typename A::T X5,
+                                           typename A::T X6, typename A::T X7)
+{
+    Stage1<typename A::T> h;
+    h.v[0] = o.mulc(X0, SVS_HW);
+    h.v[1] = o.mulc(X4, SVS_HW);
+    h.v[2] = o.add(X1, X7);
+    h.v[3] = o.sub(X1, X7);
+    h.v[4] = o.add(X2, X6);
+    h.v[5] = o.sub(X2, X6);
+    h.v[6] = o.add(X3, X5);
+    h.v[7] = o.sub(X3, X5);
+    return h;
+}
+
+// inverse tail: the remaining 46 operations; x[0..7] out
+template <class A>
+SVS_HD void dct8_inv_tail(const A& o, const Stage1<typename A::T>& h, typename A::T (&x)[8])
 {
     typedef typename A::T T;
-    const T X0 = x[0], X1 = x[S], X2 = x[2 * S], X3 = x[3 * S];
-    const T X4 = x[4 * S], X5 = x[5 * S], X6 = x[6 * S], X7 = x[7 * S];
-    const T c0 = o.mulc(X0, SVS_HW);
-    const T c4 = o.mulc(X4, SVS_HW);
+    const T c0 = h.v[0], c4 = h.v[1];
     T t1, t2;
-    t1 = o.add(X1, X7); t2 = o.sub(X1, X7);
+    t1 = h.v[2]; t2 = h.v[3];
     const T c1 = o.add(o.mulc(t2, SVS_Q1), o.mulc(t1, SVS_Q7));
     const T c7 = o.sub(o.mulc(t1, SVS_Q1), o.mulc(t2, SVS_Q7));
-    t1 = o.add(X2, X6); t2 = o.sub(X2, X6);
+    t1 = h.v[4]; t2 = h.v[5];
     const T c2 = o.add(o.mulc(t2, SVS_Q2), o.mulc(t1, SVS_Q6));
     const T c6 = o.sub(o.mulc(t1, SVS_Q2), o.mulc(t2, SVS_Q6));
-    t1 = o.add(X3, X5); t2 = o.sub(X3, X5);
+    t1 = h.v[6]; t2 = h.v[7];
     const T c3 = o.add(o.mulc(t2, SVS_Q3), o.mulc(t1, SVS_Q5));
     const T c5 = o.sub(o.mulc(t1, SVS_Q3), o.mulc(t2, SVS_Q5));
     T r1, r2;
@@ -120,13 +168,23 @@ SVS_HD void dct8_inv(const A& o, typename A::T* x)
     const T o1 = o.add(h1, tr), o5 = o.sub(h1, tr);
     const T o2 = o.add(ti, h2), o6 = o.sub(ti, h2);
     x[0] = o.add(h0, h4);
-    x[7 * S] = o.sub(h0, h4);
-    x[S] = o.sub(o1, o2);
-    x[2 * S] = o.add(o2, o1);
-    x[3 * S] = o.add(h3, h7);
-    x[4 * S] = o.sub(h3, h7);
-    x[5 * S] = o.sub(o5, o6);
-    x[6 * S] = o.add(o6, o5);
+    x[7] = o.sub(h0, h4);
+    x[1] = o.sub(o1, o2);
+    x[2] = o.add(o2, o1);
+    x[3] = o.add(h3, h7);
+    x[4] = o.sub(h3, h7);
+    x[5] = o.sub(o5, o6);
+    x[6] = o.add(o6, o5);
+}
+
+// Inverse (DCT-III, scipy idct type=2 norm='ortho'): x[0], x[S], ..., x[7S] in place.
+template <int S, class A>
+SVS_HD void dct8_inv(const A& o, typename A::T* x)
+{
+    typename A::T y[8];
+    dct8_inv_tail(o, dct8_inv_head(o, x[0], x[S], x[2 * S], x[3 * S], x[4 * S], x[5 * S], x[6 * S], x[7 * S]), y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k * S] = y[k];
 }
 
 // 2-D: axis 0 (down the columns) first, then axis 1 (config_and_setup.py:135,168).  b[u*8+v].

@@ -11,6 +11,12 @@ sys.dont_write_bytecode = True
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # SVS_TEST_LIB: run the suite against another BUILD of the library (e.g. the measurement build
+    # with the round-1 kernel families, variants/libsvs_variants.so).  Test infrastructure only.
+    alt = os.environ.get("SVS_TEST_LIB")
+    if alt:
+        import svs_b200
+        svs_b200._native.use_library(os.path.abspath(alt))
 
 
 def pytest_collection_modifyitems(config, items):

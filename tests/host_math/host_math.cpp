@@ -41,3 +41,69 @@ void hm_quant_check(double delta, const float* c, long n, long* stats)
     }
 }
 }
+
+// ---- the block-level code of the packed kernels (csrc/svs_block.cuh) on the host --------------
+// One 8x8 block per call: `px` = 8 rows x 8*ch bytes, `bits` = n payload bits (0/1 bytes).
+#include "svs_block.cuh"
+
+namespace {
+void words_of(const uint8_t* px, int ch, uint32_t* rows)
+{
+    const int P = ch == 3 ? 6 : 2;
+    for (int r = 0; r < 8; ++r)
+        for (int k = 0; k < P; ++k) {
+            uint32_t w = 0;
+            for (int b = 0; b < 4; ++b) w |= (uint32_t)px[r * 8 * ch + 4 * k + b] << (8 * b);
+            rows[r * P + k] = w;
+        }
+}
+void bytes_of(const uint32_t* w16, uint8_t* out)
+{
+    for (int k = 0; k < 16; ++k)
+        for (int b = 0; b < 4; ++b) out[4 * k + b] = (uint8_t)(w16[k] >> (8 * b));
+}
+}  // namespace
+
+extern "C" {
+// returns 0, or -1 when the packed quantiser does not cover this delta (the kernels then use the scalar path)
+int hm_blk_embed(int ch, const uint8_t* px, long nblocks, double delta, int n, const uint8_t* bits, uint8_t* stego, uint8_t* gray)
+{
+    const svs::FastQuant fq = svs::make_fast_quant(delta);
+    if (!fq.embed_ok || (double)(float)delta != delta) return -1;
+    const blk::QuantRegs Q = blk::make_quant_regs(fq, (float)delta);
+    for (long b = 0; b < nblocks; ++b) {
+        uint32_t rows[48], s[16], g[16], w0 = 0, w1 = 0;
+        words_of(px + b * 64 * ch, ch, rows);
+        for (int i = 0; i < n; ++i) {
+            if (i < 32) w0 |= (uint32_t)(bits[b * n + i] & 1) << (31 - i);
+            else w1 |= (uint32_t)(bits[b * n + i] & 1) << (63 - i);
+        }
+        if (ch == 3) { if (n == 63) blk::block_embed<3, true, true>(rows, 0x4B000000u, Q, n, w0, w1, s, g); else blk::block_embed<3, false, true>(rows, 0x4B000000u, Q, n, w0, w1, s, g); }
+        else         { if (n == 63) blk::block_embed<1, true, true>(rows, 0x4B000000u, Q, n, w0, w1, s, g); else blk::block_embed<1, false, true>(rows, 0x4B000000u, Q, n, w0, w1, s, g); }
+        bytes_of(s, stego + b * 64);
+        bytes_of(g, gray + b * 64);
+    }
+    return 0;
+}
+
+int hm_blk_extract(int ch, const uint8_t* px, long nblocks, double delta, int n, uint8_t* bits_out)
+{
+    const svs::FastQuant fq = svs::make_fast_quant(delta);
+    if (!fq.extract_ok) return -1;
+    const blk::QuantRegs Q = blk::make_quant_regs(fq, (float)delta);
+    const int np = (n + 1 + 15) / 16;
+    for (long b = 0; b < nblocks; ++b) {
+        uint32_t rows[48], hi = 0, lo = 0;
+        words_of(px + b * 64 * ch, ch, rows);
+#define HM_X(CH, NP) blk::block_extract<CH, NP>(rows, 0x4B000000u, Q, n, hi, lo)
+        if (ch == 3) { if (np == 1) HM_X(3, 1); else if (np == 2) HM_X(3, 2); else if (np == 3) HM_X(3, 3); else HM_X(3, 4); }
+        else         { if (np == 1) HM_X(1, 1); else if (np == 2) HM_X(1, 2); else if (np == 3) HM_X(1, 3); else HM_X(1, 4); }
+#undef HM_X
+        for (int i = 0; i < n; ++i) bits_out[b * n + i] = (uint8_t)(i < 32 ? (hi >> (31 - i)) & 1u : (lo >> (63 - i)) & 1u);
+        // nothing may be set beyond bit n
+        const unsigned long long s = ((unsigned long long)hi << 32) | lo;
+        if (n < 64 && (s << n) != 0) return -2;
+    }
+    return 0;
+}
+}

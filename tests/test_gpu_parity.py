@@ -85,14 +85,25 @@ def test_dropin_edge_semantics():
 
 
 # ------------------------------------------------------------------ batched API vs the C oracle
-@pytest.fixture(params=["row", "tile", "lockstep", "scalar"])
+FAMILIES = {"scalar": 1, "lockstep": 2, "tile": 3, "row": 4, "block": 5}
+
+
+def _select_family(name):
+    """Switch the library to one kernel family; skips when this build does not carry it (the
+    round-1 organisations are only in -DSVS_WITH_VARIANTS measurement builds)."""
+    prev = svs_b200.lib().svs_debug_kernel_family(FAMILIES[name])
+    if prev < 0:
+        pytest.skip("kernel family %r is not part of this build" % name)
+    return prev
+
+
+@pytest.fixture(params=["block", "scalar", "lockstep", "tile", "row"])
 def kernel_family(request):
-    """Run a test through each kernel family: packed row (8 lanes per block pair), packed tile,
-    packed lockstep, scalar."""
-    mode = {"scalar": 1, "lockstep": 2, "tile": 3, "row": 4}[request.param]
-    prev = svs_b200.lib().svs_debug_force_scalar(mode)
+    """Run a test through each kernel family of the loaded build: packed block (one block per
+    thread) and scalar always; lockstep / tile / row in measurement builds."""
+    prev = _select_family(request.param)
     yield request.param
-    svs_b200.lib().svs_debug_force_scalar(prev)
+    svs_b200.lib().svs_debug_kernel_family(prev)
 
 
 @pytest.mark.parametrize("shape,delta,n,frac", [
@@ -199,12 +210,12 @@ def test_bgr_stego_store_contiguous_batches(shape, n, kernel_family):
     assert np.array_equal(ext3, oc.extract_frames(stego, delta, n))
 
 
-@pytest.mark.parametrize("family", ["lockstep", "row"])
+@pytest.mark.parametrize("family", ["block", "lockstep", "row"])
 def test_extract_with_peer_scatter_on_one_device(family):
     """svs_extract_frames_scatter with "peers" that are further buffers on the same GPU: every
     buffer receives the rows (the 2-GPU NVLink variant is tests/test_multi_gpu.py)."""
     torch = _torch()
-    prev = svs_b200.lib().svs_debug_force_scalar({"lockstep": 2, "row": 4}[family])
+    prev = _select_family(family)
     try:
         frames = synth_frames("scatter", (5, 64, 128), 0, 256)
         n, delta = 63, 20
@@ -218,7 +229,7 @@ def test_extract_with_peer_scatter_on_one_device(family):
         with pytest.raises(ValueError):                       # 16 peers: more than the kernels take
             svs_b200.extract_frames(_dev(frames), delta, n, out=bufs[0], peer_ptrs=[bufs[1].data_ptr()] * 16)
     finally:
-        svs_b200.lib().svs_debug_force_scalar(prev)
+        svs_b200.lib().svs_debug_kernel_family(prev)
 
 
 def test_extract_byte_store_path_matches_word_store_path():
