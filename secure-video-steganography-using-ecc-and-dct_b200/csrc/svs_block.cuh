@@ -60,7 +60,7 @@ struct QuantRegs {
     P2 rr, kx;                          // extract
     uint32_t emask, ebit, xmask;
     int erot, xk;
-    float d, r, negzero;                // delta32, RN(1/delta32), -0.0f
+    float d, r;                         // delta32, RN(1/delta32)
     float r2s, kes, kxs;                // scalar copies for the repair paths
 };
 SVS_HD QuantRegs make_quant_regs(const FastQuant& q, float delta32)
@@ -70,7 +70,7 @@ SVS_HD QuantRegs make_quant_regs(const FastQuant& q, float delta32)
     c.rr = hw::pk(q.r, q.r); c.kx = hw::pk(q.kx, q.kx);
     c.emask = q.emask; c.ebit = q.ebit; c.xmask = q.xmask;
     c.erot = q.erot; c.xk = q.xk;
-    c.d = delta32; c.r = q.r; c.negzero = q.negzero;
+    c.d = delta32; c.r = q.r;
     c.r2s = q.r2; c.kes = q.ke; c.kxs = q.kx;
     return c;
 }
@@ -78,8 +78,9 @@ SVS_HD QuantRegs make_quant_regs(const FastQuant& q, float delta32)
 // ------------------------------------------------------------------------------------------
 // input: one image row of the block -> 4 column pairs of exact floats
 // ------------------------------------------------------------------------------------------
-// (2^23 + byte SEL of v) as float bits: one PRMT  [v.bSEL, 0x00, 0x00, 0x4B]
-SVS_HD uint32_t magic_byte(uint32_t v, uint32_t magic_hi, int sel) { return hw::byte_perm(v, magic_hi, 0x7540u | (uint32_t)sel); }
+// (2^23 + 256 * byte SEL of v) as float bits: one PRMT  [0x00, v.bSEL, 0x00, 0x4B].  The axis-0
+// pass works on these directly (svs_math.cuh: dct8_fwd_tail_impl<true>), no conversion arithmetic.
+SVS_HD uint32_t magic_byte(uint32_t v, uint32_t magic_hi, int sel) { return hw::byte_perm(v, magic_hi, 0x7504u | ((uint32_t)sel << 4)); }
 
 // BGR -> gray of the 8 pixels of a row held in six words: cv2 BGR2GRAY,
 // (3735 B + 19235 G + 9798 R + 16384) >> 15 (config_and_setup.py:112), computed as two dp2a per
@@ -109,17 +110,17 @@ SVS_HD void row_gray_words(const uint32_t* w, uint32_t& glo, uint32_t& ghi)
 }
 
 // CH == 1: w[0..1] are the 8 gray bytes; CH == 3: w[0..5] are the 24 BGR bytes.
-// c[0..3] = column pairs of the row; glo/ghi = the row's gray bytes (only built when WANT_GRAY).
+// c[0..3] = column pairs of the row as 2^23 + 256 * gray; glo/ghi = the row's gray bytes (only
+// built when WANT_GRAY).
 template <int CH, bool WANT_GRAY>
 SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& glo, uint32_t& ghi)
 {
-    const P2 unbias = hw::pk(-8388608.0f, -8388608.0f);
     if (CH == 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t a = magic_byte(w[(2 * j) >> 2], magic_hi, (2 * j) & 3);
             const uint32_t b = magic_byte(w[(2 * j + 1) >> 2], magic_hi, (2 * j + 1) & 3);
-            c[j] = hw::add2(hw::pku(a, b), unbias);                                   // exact
+            c[j] = hw::pku(a, b);
         }
         if (WANT_GRAY) { glo = w[0]; ghi = w[1]; }
     } else {
@@ -128,7 +129,7 @@ SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& 
         bgr_row_sums(v, s);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            c[j] = hw::add2(hw::pku(hw::byte_perm(s[2 * j], magic_hi, 0x7542u), hw::byte_perm(s[2 * j + 1], magic_hi, 0x7542u)), unbias);
+            c[j] = hw::pku(hw::byte_perm(s[2 * j], magic_hi, 0x7524u), hw::byte_perm(s[2 * j + 1], magic_hi, 0x7524u));
         if (WANT_GRAY) {
             glo = hw::byte_perm(hw::byte_perm(s[0], s[1], 0x0062u), hw::byte_perm(s[2], s[3], 0x0062u), 0x5410u);
             ghi = hw::byte_perm(hw::byte_perm(s[4], s[5], 0x0062u), hw::byte_perm(s[6], s[7], 0x0062u), 0x5410u);
@@ -139,11 +140,17 @@ SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& 
 // ------------------------------------------------------------------------------------------
 // the four passes
 // ------------------------------------------------------------------------------------------
-// axis 0, forward: four packed transforms down the column pairs, in place
+// axis 0, forward: four packed transforms down the column pairs, in place.  In: 2^23 + 256 *
+// pixel (row_to_pairs); out: the coefficients of the axis-0 pass, as the reference has them.
 SVS_HD void columns_fwd(const PackedOps& po, P2 (&c)[32])
 {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) svs::dct8_fwd<4>(po, c + j);
+    for (int j = 0; j < 4; ++j) {
+        P2 X[8];
+        svs::dct8_fwd_tail_impl<true>(po, svs::dct8_fwd_head(po, c[j], c[4 + j], c[8 + j], c[12 + j], c[16 + j], c[20 + j], c[24 + j], c[28 + j]), X);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[4 * u + j] = X[u];
+    }
 }
 
 // Only the first 2*NP coefficient rows of axis 0 (extraction with few coefficients per block:
@@ -155,7 +162,7 @@ SVS_HD void columns_fwd_pruned(const PackedOps& po, P2 (&c)[32])
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         P2 X[8];
-        svs::dct8_fwd_tail(po, svs::dct8_fwd_head(po, c[j], c[4 + j], c[8 + j], c[12 + j], c[16 + j], c[20 + j], c[24 + j], c[28 + j]), X);
+        svs::dct8_fwd_tail_impl<true>(po, svs::dct8_fwd_head(po, c[j], c[4 + j], c[8 + j], c[12 + j], c[16 + j], c[20 + j], c[24 + j], c[28 + j]), X);
 #pragma unroll
         for (int u = 0; u < 2 * NP; ++u) c[4 * u + j] = X[u];
     }
@@ -401,18 +408,32 @@ SVS_HD void block_input(const uint32_t* rows, uint32_t magic_hi, P2 (&c)[32], ui
     }
 }
 
-// c: the block as column pairs (destroyed).  stego: 16 words (row r at [2r], [2r+1]).  Every
-// block coming here takes all n bits.
+// Forward 2-D transform of the block (column pairs c, destroyed) and embedding of its n payload
+// bits: q = the quantised coefficients as row pairs.  Every block coming here takes all n bits.
+// SVS_BLK_QPIPE: the axis-1 transform of row pair i+1 is issued before row pair i is quantised,
+// so that FP32 work and the quantiser's integer work sit in the same basic block.
+#ifndef SVS_BLK_QPIPE
+#define SVS_BLK_QPIPE 0
+#endif
 template <bool NFULL>
-SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t* stego)
+SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, P2 (&q)[32])
 {
-    PackedOps po;
-    po.negzero = hw::pk(Q.negzero, Q.negzero);
+    const PackedOps po;
     const ScalarOps so;
     columns_fwd(po, c);
     const int pre = (Q.erot - 31) & 31;
     const uint32_t p0 = hw::funnel_l(w0, w0, pre), p1 = hw::funnel_l(w1, w1, pre);
-    P2 q[32];
+#if SVS_BLK_QPIPE
+    P2 X[2][8];
+    rows_fwd_pair(po, so, c, X[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < 3) rows_fwd_pair(po, so, c + 8 * (i + 1), X[(i + 1) & 1]);
+        if (NFULL || 16 * i - 1 < n) quant_embed_pair<NFULL>(i, X[i & 1], Q, n, w0, w1, p0, p1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) q[8 * i + v] = X[i & 1][v];
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         P2 X[8];
@@ -421,6 +442,16 @@ SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w
 #pragma unroll
         for (int v = 0; v < 8; ++v) q[8 * i + v] = X[v];
     }
+#endif
+}
+
+// Inverse 2-D transform of the row pairs q (destroyed) and conversion to bytes:
+// stego = 16 words, row r at [2r], [2r+1].
+SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
+{
+    const PackedOps po;
+    const ScalarOps so;
+    P2 c[32];
 #pragma unroll
     for (int j = 0; j < 4; ++j) columns_inv_pair(po, so, q, j, c);
 #pragma unroll
@@ -441,6 +472,14 @@ SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w
     }
 }
 
+template <bool NFULL>
+SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t* stego)
+{
+    P2 q[32];
+    block_forward_quant<NFULL>(c, Q, n, w0, w1, q);
+    block_inverse(q, stego);
+}
+
 template <int CH, bool NFULL, bool WANT_GRAY>
 SVS_HD void block_embed(const uint32_t* rows, uint32_t magic_hi, const QuantRegs& Q, int n, uint32_t w0, uint32_t w1,
                         uint32_t* stego, uint32_t* gray)
@@ -456,13 +495,23 @@ SVS_HD void block_embed(const uint32_t* rows, uint32_t magic_hi, const QuantRegs
 template <int NP>
 SVS_HD void block_extract_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t& hi, uint32_t& lo)
 {
-    PackedOps po;
-    po.negzero = hw::pk(Q.negzero, Q.negzero);
+    const PackedOps po;
     const ScalarOps so;
     if (NP == 4) columns_fwd(po, c);
     else columns_fwd_pruned<NP>(po, c);
     hi = 0;
     lo = 0;
+#if SVS_BLK_QPIPE
+    P2 X[2][8];
+    rows_fwd_pair(po, so, c, X[0]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        if (i + 1 < NP) rows_fwd_pair(po, so, c + 8 * (i + 1), X[(i + 1) & 1]);
+        const uint32_t rows2 = quant_extract_pair(i, X[i & 1], Q, n);
+        place_row(2 * i, rows2 & 0xffu, hi, lo);
+        place_row(2 * i + 1, rows2 >> 16, hi, lo);
+    }
+#else
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         P2 X[8];
@@ -471,6 +520,7 @@ SVS_HD void block_extract_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
         place_row(2 * i, rows2 & 0xffu, hi, lo);
         place_row(2 * i + 1, rows2 >> 16, hi, lo);
     }
+#endif
     // bits n.. of the string are not part of the stream (config_and_setup.py:138-140)
     if (n < 32) { hi &= ~(0xffffffffu >> n); lo = 0; }
     else if (n < 64) lo &= n == 32 ? 0u : ~(0xffffffffu >> (n - 32));
@@ -498,10 +548,8 @@ SVS_HD void block_extract(const uint32_t* rows, uint32_t magic_hi, const QuantRe
 //   0  LDG at the top of the group (the warp waits for HBM once per group);
 //   1  the same, plus prefetch.global.L2 of the NEXT group's rows;
 //   2  the next group's rows are requested as soon as the current ones have been converted to
-//      floats: with cp.async into a thread-private shared-memory slot (BGR input: 48 words;
-//      gray input of embed: 16), or straight into the 16 registers that just became free (gray
-//      input of extract) - either way they arrive while the current group is being transformed
-//      (default).
+//      floats, with cp.async into a thread-private shared-memory slot (BGR input: 48 words,
+//      gray input: 16): they arrive while the current group is being transformed (default).
 #ifndef SVS_BLK_STAGE
 #define SVS_BLK_STAGE 2
 #endif
@@ -511,11 +559,11 @@ constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kBlkStage = SVS_BLK_STAGE;
 constexpr int kMaxPeers = 15;
 
-// Which instantiations stage through shared memory (the rest of mode 2 reuse the row registers):
-// BGR input always (48 words), gray input only in embed (its 16 row words + the payload words
-// do not fit next to the 64 coefficient registers).
+// Mode 2 stages through shared memory in every instantiation: a load in flight INTO REGISTERS
+// across the quantiser would make its rare out-of-line repair call wait for HBM (the callee
+// saves the registers the load is going to write) - measured: 8 % of the warp time.
 template <int CH, bool EMBED>
-constexpr bool blk_uses_smem() { return kBlkStage == 2 && (CH == 3 || EMBED); }
+constexpr bool blk_uses_smem() { return kBlkStage == 2; }
 // dynamic shared memory of a kernel instantiation: the cp.async slots, 8 bytes x rows x words x threads
 template <int CH, bool EMBED>
 constexpr int blk_smem_bytes() { return blk_uses_smem<CH, EMBED>() ? 8 * (CH == 3 ? 3 : 1) * 8 * kBlkThreads : 0; }
@@ -726,15 +774,16 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
         Where wn = w;
         if (more) {
             wn = locate(G, gn, lane);
-            if (kStaged) {
-                stage_request<CH>(G, wn, slot0);
-                pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
-            } else if (kBlkStage == 1) {
-                prefetch_rows_l2<CH>(G, wn);
-            }
+            if (kStaged) stage_request<CH>(G, wn, slot0);
+            else if (kBlkStage == 1) prefetch_rows_l2<CH>(G, wn);
         }
 
-        block_embed_pairs<NFULL>(c, Q, n, w0, w1, stego);
+        P2 q[32];
+        block_forward_quant<NFULL>(c, Q, n, w0, w1, q);
+        // (only now: a load in flight across the quantiser would make its rare out-of-line repair
+        // call wait for HBM - the callee saves the registers the load is going to write)
+        if (more && kStaged) pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
+        block_inverse(q, stego);
         if (w.ok) {
             uint8_t* dst = a.stego + w.f * a.stego_frame_stride + (long long)(w.by * 8) * a.stego_row_stride + w.bx * (8 * OUT_CH);
 #pragma unroll
@@ -809,13 +858,10 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(c
 
     Where w = locate(G, g, lane);
     uint32_t rows[CH == 3 ? 48 : 16];
-    if (kStaged) {
-        if (CH == 3) stage_request<CH>(G, w, slot0);
-        else load_rows<CH>(G, w, rows);
-    }
+    if (kStaged) stage_request<CH>(G, w, slot0);
     for (;;) {
         if (!kStaged) load_rows<CH>(G, w, rows);
-        else if (CH == 3) stage_fetch<CH>(slot0, rows);
+        else stage_fetch<CH>(slot0, rows);
         pack[warp][lane] = 0;
         pack[warp][lane + 32] = 0;
         P2 c[32];
@@ -826,12 +872,8 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(c
         Where wn = w;
         if (more) {
             wn = locate(G, gn, lane);
-            if (kStaged) {
-                if (CH == 3) stage_request<CH>(G, wn, slot0);
-                else load_rows<CH>(G, wn, rows);
-            } else if (kBlkStage == 1) {
-                prefetch_rows_l2<CH>(G, wn);
-            }
+            if (kStaged) stage_request<CH>(G, wn, slot0);
+            else if (kBlkStage == 1) prefetch_rows_l2<CH>(G, wn);
         }
 
         uint32_t hi, lo;

@@ -74,6 +74,7 @@ struct PackedOps {
     __device__ __forceinline__ T add(T a, T b) const { return add2(a, b); }
     __device__ __forceinline__ T sub(T a, T b) const { return sub2(a, b); }
     __device__ __forceinline__ T mulc(T a, float c) const { return fma2(a, pk(c, c), negzero); }
+    __device__ __forceinline__ void bfly(T a, T b, T& sum, T& diff) const { sum = add2(a, b); diff = sub2(a, b); }
 };
 
 using svs::FastQuant;            // host-computed constants of the division-free quantiser (svs_quant.h)

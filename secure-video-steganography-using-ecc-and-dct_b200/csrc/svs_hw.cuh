@@ -118,16 +118,34 @@ SVS_HD float lo_of(P2 p) { float a, b; unpkf(p, a, b); return a; }
 SVS_HD float hi_of(P2 p) { float a, b; unpkf(p, a, b); return b; }
 SVS_HD uint32_t bswap(uint32_t v) { return byte_perm(v, 0, 0x0123); }
 
-// Arithmetic policy for svs_math.cuh on packed pairs.  A product must round on its own before it
-// is added to anything, but ptxas contracts mul.f32x2 + add.f32x2 regardless of .rn; fma(a, c,
-// -0.0) with a -0.0 the compiler cannot see through (it arrives as a kernel argument) is an
-// exact multiply that nothing can be fused into.
+// Arithmetic policy for svs_math.cuh on packed pairs.
+//
+// A product must round on its own before it is added to anything, but ptxas contracts
+// mul.f32x2 + add.f32x2 into one FFMA2 regardless of .rn and --fmad=false.  So products are
+// written fma(a, c, +0.0): the addend is the zero register (RZ) - no register-file read, which
+// matters because operand delivery is what these kernels are bound by (profiles/rf_model.py) -
+// and since fma(a, c, +0.0) is NOT the same function as a * c (it returns +0 where the product
+// is -0) the compiler can neither turn it back into a multiply nor fuse an addition into it.
+// The one difference, the sign of an exact zero, cannot reach a result: a zero of either sign
+// added to a non-zero value, quantised (fma(+-0, r, k) = k), divided (rint(+-0 / d) = 0) or
+// converted to a byte gives the same bits.  tests/test_block_host.py runs this very arithmetic
+// against the oracle on the CPU, the -m gpu tests against the scalar kernels' true multiplies.
 struct PackedOps {
     typedef P2 T;
-    P2 negzero;
     SVS_HDM T add(T a, T b) const { return add2(a, b); }
     SVS_HDM T sub(T a, T b) const { return sub2(a, b); }
-    SVS_HDM T mulc(T a, float c) const { return fma2(a, pk(c, c), negzero); }
+    SVS_HDM T mulc(T a, float c) const { return fma2(a, pk(c, c), pku(0u, 0u)); }
+    SVS_HDM T cst(float c) const { return pk(c, c); }
+    // sum = a + b, diff = a - b back to back (see ScalarOps::bfly)
+    SVS_HDM void bfly(T a, T b, T& sum, T& diff) const
+    {
+#if defined(__CUDA_ARCH__)
+        asm("add.rn.f32x2 %0, %2, %3;\n\tsub.rn.f32x2 %1, %2, %3;" : "=&l"(sum.v), "=&l"(diff.v) : "l"(a.v), "l"(b.v));
+#else
+        sum = add2(a, b);
+        diff = sub2(a, b);
+#endif
+    }
 };
 
 }  // namespace hw

@@ -44,10 +44,20 @@ struct ScalarOps {
     SVS_HDM T add(T a, T b) const { return __fadd_rn(a, b); }
     SVS_HDM T sub(T a, T b) const { return __fsub_rn(a, b); }
     SVS_HDM T mulc(T a, float c) const { return __fmul_rn(a, c); }
+    SVS_HDM T cst(float c) const { return c; }
+    // sum = a + b, diff = a - b, emitted back to back: the second instruction finds both operands
+    // in the operand-reuse cache instead of the register file (profiles/microbench/coissue.cu:
+    // register-file read bandwidth, not the FP32 pipe, is what the packed kernels run out of)
+    SVS_HDM void bfly(T a, T b, T& sum, T& diff) const
+    {
+        asm("add.rn.f32 %0, %2, %3;\n\tsub.rn.f32 %1, %2, %3;" : "=&f"(sum), "=&f"(diff) : "f"(a), "f"(b));
+    }
 #else
     SVS_HDM T add(T a, T b) const { return a + b; }
     SVS_HDM T sub(T a, T b) const { return a - b; }
     SVS_HDM T mulc(T a, float c) const { return a * c; }
+    SVS_HDM T cst(float c) const { return c; }
+    SVS_HDM void bfly(T a, T b, T& sum, T& diff) const { sum = a + b; diff = a - b; }
 #endif
 };
 
@@ -68,48 +78,60 @@ SVS_HD Stage1<typename A::T> dct8_fwd_head(const A& o, typename A::T x0, typenam
                                            typename A::T x6, typename A::T x7)
 {
     Stage1<typename A::T> h;
-    h.v[0] = o.add(x0, x7);
-    h.v[1] = o.add(x1, x2);
-    h.v[2] = o.sub(x2, x1);
-    h.v[3] = o.add(x3, x4);
-    h.v[4] = o.sub(x4, x3);
-    h.v[5] = o.add(x5, x6);
-    h.v[6] = o.sub(x6, x5);
-    h.v[7] = o.sub(x0, x7);
+    o.bfly(x0, x7, h.v[0], h.v[7]);
+    o.bfly(x2, x1, h.v[1], h.v[2]);              // x1 + x2 (commutative: same bits), x2 - x1
+    o.bfly(x4, x3, h.v[3], h.v[4]);
+    o.bfly(x6, x5, h.v[5], h.v[6]);
     return h;
 }
 
-// forward tail: the remaining 46 operations; X[0..7] out
+// forward tail: the remaining 46 operations; X[0..7] out.
+//
+// BIASED (axis-0 pass of the packed kernels, svs_block.cuh): the 8 inputs of the head were not
+// the pixels p but 2^23 + 256 p - a byte dropped into the mantissa of 2^23 by one PRMT, no
+// subtraction.  Every operation up to and including e0..e7's integer part is then still exact:
+// differences cancel the 2^23, sums double it (2^24 + 256 (p + p'), a multiple of the ulp), and
+// the only stage-3 value that still carries it is e0 = 2^26 + 256 (sum of the 8 pixels), one
+// subtraction.  All values are 256 x what the reference holds at that point; scaling by a power
+// of two commutes with every rounding (no underflow: non-zero magnitudes stay > 2^-100), so the
+// 2^-8 is folded into the constants of the final products.  Net: 7 operations fewer per
+// transform than converting each byte to a float first.
+template <bool BIASED, class A>
+SVS_HD void dct8_fwd_tail_impl(const A& o, const Stage1<typename A::T>& h, typename A::T (&X)[8])
+{
+    typedef typename A::T T;
+    constexpr float S = BIASED ? 0x1p-8f : 1.0f;
+    const T s07 = h.v[0], a1 = h.v[1], a2 = h.v[2], a3 = h.v[3], a4 = h.v[4], a5 = h.v[5], a6 = h.v[6], d07 = h.v[7];
+    T h1, tr, ti, h2, h6, h5, p0, m0, p1, m1, e0, e4, e6, e2, e1, e5, e7, e3;
+    o.bfly(a1, a5, h1, tr);
+    o.bfly(a2, a6, ti, h2);
+    const T wti = o.mulc(ti, SVS_W), wtr = o.mulc(tr, SVS_W);
+    o.bfly(wtr, wti, h6, h5);                    // wti + wtr, wtr - wti
+    o.bfly(s07, a3, p0, m0);
+    o.bfly(d07, a4, m1, p1);                     // d07 + a4, d07 - a4
+    o.bfly(p0, h1, e0, e4);
+    if constexpr (BIASED) e0 = o.sub(e0, o.cst(67108864.0f));          // 8 x 2^23, exact
+    o.bfly(m0, h2, e6, e2);
+    o.bfly(p1, h5, e1, e5);
+    o.bfly(m1, h6, e7, e3);
+    T t1, t2;
+    t1 = o.add(o.mulc(e7, SVS_Q1 * S), o.mulc(e1, SVS_Q7 * S));
+    t2 = o.sub(o.mulc(e1, SVS_Q1 * S), o.mulc(e7, SVS_Q7 * S));
+    o.bfly(t1, t2, X[1], X[7]);
+    t1 = o.add(o.mulc(e6, SVS_Q2 * S), o.mulc(e2, SVS_Q6 * S));
+    t2 = o.sub(o.mulc(e2, SVS_Q2 * S), o.mulc(e6, SVS_Q6 * S));
+    o.bfly(t1, t2, X[2], X[6]);
+    t1 = o.add(o.mulc(e5, SVS_Q3 * S), o.mulc(e3, SVS_Q5 * S));
+    t2 = o.sub(o.mulc(e3, SVS_Q3 * S), o.mulc(e5, SVS_Q5 * S));
+    o.bfly(t1, t2, X[3], X[5]);
+    X[4] = o.mulc(e4, SVS_HW * S);
+    X[0] = o.mulc(e0, SVS_HW * S);
+}
+
 template <class A>
 SVS_HD void dct8_fwd_tail(const A& o, const Stage1<typename A::T>& h, typename A::T (&X)[8])
 {
-    typedef typename A::T T;
-    const T s07 = h.v[0], a1 = h.v[1], a2 = h.v[2], a3 = h.v[3], a4 = h.v[4], a5 = h.v[5], a6 = h.v[6], d07 = h.v[7];
-    const T h1 = o.add(a1, a5), tr = o.sub(a1, a5);
-    const T ti = o.add(a2, a6), h2 = o.sub(a2, a6);
-    const T wti = o.mulc(ti, SVS_W), wtr = o.mulc(tr, SVS_W);
-    const T h6 = o.add(wti, wtr), h5 = o.sub(wtr, wti);
-    const T p0 = o.add(s07, a3), m0 = o.sub(s07, a3);
-    const T p1 = o.sub(d07, a4), m1 = o.add(d07, a4);
-    const T e0 = o.add(p0, h1), e4 = o.sub(p0, h1);
-    const T e6 = o.add(m0, h2), e2 = o.sub(m0, h2);
-    const T e1 = o.add(p1, h5), e5 = o.sub(p1, h5);
-    const T e7 = o.add(m1, h6), e3 = o.sub(m1, h6);
-    T t1, t2;
-    t1 = o.add(o.mulc(e7, SVS_Q1), o.mulc(e1, SVS_Q7));
-    t2 = o.sub(o.mulc(e1, SVS_Q1), o.mulc(e7, SVS_Q7));
-    X[1] = o.add(t1, t2);
-    X[7] = o.sub(t1, t2);
-    t1 = o.add(o.mulc(e6, SVS_Q2), o.mulc(e2, SVS_Q6));
-    t2 = o.sub(o.mulc(e2, SVS_Q2), o.mulc(e6, SVS_Q6));
-    X[2] = o.add(t1, t2);
-    X[6] = o.sub(t1, t2);
-    t1 = o.add(o.mulc(e5, SVS_Q3), o.mulc(e3, SVS_Q5));
-    t2 = o.sub(o.mulc(e3, SVS_Q3), o.mulc(e5, SVS_Q5));
-    X[3] = o.add(t1, t2);
-    X[5] = o.sub(t1, t2);
-    X[4] = o.mulc(e4, SVS_HW);
-    X[0] = o.mulc(e0, SVS_HW);
+    dct8_fwd_tail_impl<false>(o, h, X);
 }
 
 // Forward DCT-II (norm='ortho'): x[0], x[S], ..., x[7S] in place.
@@ -131,12 +153,9 @@ SVS_HD Stage1<typename A::T> dct8_inv_head(const A& o, typename A::T X0, typenam
     Stage1<typename A::T> h;
     h.v[0] = o.mulc(X0, SVS_HW);
     h.v[1] = o.mulc(X4, SVS_HW);
-    h.v[2] = o.add(X1, X7);
-    h.v[3] = o.sub(X1, X7);
-    h.v[4] = o.add(X2, X6);
-    h.v[5] = o.sub(X2, X6);
-    h.v[6] = o.add(X3, X5);
-    h.v[7] = o.sub(X3, X5);
+    o.bfly(X1, X7, h.v[2], h.v[3]);
+    o.bfly(X2, X6, h.v[4], h.v[5]);
+    o.bfly(X3, X5, h.v[6], h.v[7]);
     return h;
 }
 
@@ -156,25 +175,21 @@ SVS_HD void dct8_inv_tail(const A& o, const Stage1<typename A::T>& h, typename A
     t1 = h.v[6]; t2 = h.v[7];
     const T c3 = o.add(o.mulc(t2, SVS_Q3), o.mulc(t1, SVS_Q5));
     const T c5 = o.sub(o.mulc(t1, SVS_Q3), o.mulc(t2, SVS_Q5));
-    T r1, r2;
-    r1 = o.add(c6, c2); const T h2 = o.sub(c6, c2);
-    r2 = o.add(c0, c4); const T h1 = o.sub(c0, c4);
-    const T h0 = o.add(r2, r1), h3 = o.sub(r2, r1);
-    r1 = o.add(c7, c3); const T h6 = o.sub(c7, c3);
-    r2 = o.add(c1, c5); const T h5 = o.sub(c1, c5);
-    const T h4 = o.add(r2, r1), h7 = o.sub(r2, r1);
+    T r1, r2, h0, h1, h2, h3, h4, h5, h6, h7, tr, ti, o1, o2, o5, o6;
+    o.bfly(c6, c2, r1, h2);
+    o.bfly(c0, c4, r2, h1);
+    o.bfly(r2, r1, h0, h3);
+    o.bfly(c7, c3, r1, h6);
+    o.bfly(c1, c5, r2, h5);
+    o.bfly(r2, r1, h4, h7);
     const T wh5 = o.mulc(h5, SVS_W), wh6 = o.mulc(h6, SVS_W);
-    const T tr = o.add(wh5, wh6), ti = o.sub(wh6, wh5);
-    const T o1 = o.add(h1, tr), o5 = o.sub(h1, tr);
-    const T o2 = o.add(ti, h2), o6 = o.sub(ti, h2);
-    x[0] = o.add(h0, h4);
-    x[7] = o.sub(h0, h4);
-    x[1] = o.sub(o1, o2);
-    x[2] = o.add(o2, o1);
-    x[3] = o.add(h3, h7);
-    x[4] = o.sub(h3, h7);
-    x[5] = o.sub(o5, o6);
-    x[6] = o.add(o6, o5);
+    o.bfly(wh6, wh5, tr, ti);                    // wh5 + wh6, wh6 - wh5
+    o.bfly(h1, tr, o1, o5);
+    o.bfly(ti, h2, o2, o6);
+    o.bfly(h0, h4, x[0], x[7]);
+    o.bfly(o1, o2, x[2], x[1]);                  // o2 + o1, o1 - o2
+    o.bfly(h3, h7, x[3], x[4]);
+    o.bfly(o5, o6, x[6], x[5]);                  // o6 + o5, o5 - o6
 }
 
 // Inverse (DCT-III, scipy idct type=2 norm='ortho'): x[0], x[S], ..., x[7S] in place.
