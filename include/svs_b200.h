@@ -106,7 +106,11 @@ int svs_extract_frames_multicast(const uint8_t* d_frames, int channels, int64_t 
 /*
  * mode == 'embed' for a batch (config_and_setup.py:129-158,166-172).
  * Payload bit i of the batch is bit (payload_bit_offset + i) of d_payload (MSB-first);
- * payload_total_bits bits are available.  d_payload must be 4-byte aligned.
+ * payload_total_bits bits are available.  d_payload must be 4-byte aligned, and the buffer must be
+ * readable up to the end of the 32-bit word that holds its last bit (the kernels load whole
+ * words; bits past payload_bit_offset + payload_total_bits are never used).  Pad a buffer whose
+ * byte length is not a multiple of 4 - svs_b200.embed_frames (Python) and svs_embed_frames_host
+ * do so themselves.
  * Per block: float32 DCT-II, q = int(round(c/delta)), q' = q - (q mod 2) + bit on the first k
  * coefficients (k = bits left, at most n), c' = float32(q'*delta), DCT-III, clip to [0,255],
  * truncate.  Blocks after the payload end are copied as gray; the block in which it ends is

@@ -1119,6 +1119,18 @@ int sync_all(svs_ctx* c)
     }
     return SVS_OK;
 }
+
+// Error exit of a chunk loop: copies of earlier chunks may still be reading / writing the
+// caller's host buffers, so the streams are drained (result ignored, the message of `rc` is kept)
+// before the caller gets its buffers back.
+int drain_and_return(svs_ctx* c, int rc)
+{
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep);
+    for (auto& s : c->slot) cudaStreamSynchronize(s.stream);
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+}
 }  // namespace
 
 int svs_ctx_create(int device, int64_t staging_bytes_hint, svs_ctx** out)
@@ -1187,15 +1199,15 @@ int svs_extract_frames_host(svs_ctx* c, const uint8_t* h_frames, int channels, i
     for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
         svs_slot& s = c->slot[k % 3];
         const long long nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        if (int rc = ensure(s.buf[0], s.cap[0], (size_t)(nf * in_bytes))) return rc;
-        if (int rc = ensure(s.buf[1], s.cap[1], (size_t)(nf * dev_bits_stride))) return rc;
+        if (int rc = ensure(s.buf[0], s.cap[0], (size_t)(nf * in_bytes))) return drain_and_return(c, rc);
+        if (int rc = ensure(s.buf[1], s.cap[1], (size_t)(nf * dev_bits_stride))) return drain_and_return(c, rc);
         cudaError_t e = copy_frames_in(s.buf[0], h_frames + f0 * frame_stride, nf, height, row_bytes, frame_stride, row_stride, s.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "host->device frame copy");
+        if (e != cudaSuccess) return drain_and_return(c, cuda_fail(e, "host->device frame copy"));
         if (int rc = svs_extract_frames(s.buf[0], channels, nf, height, width, in_bytes, row_bytes, delta, num_ac,
-                                        s.buf[1], dev_bits_stride, s.stream)) return rc;
+                                        s.buf[1], dev_bits_stride, s.stream)) return drain_and_return(c, rc);
         e = cudaMemcpy2DAsync(h_bits_out + f0 * bits_frame_stride, (size_t)bits_frame_stride, s.buf[1], (size_t)dev_bits_stride,
                               (size_t)frame_bytes, (size_t)nf, cudaMemcpyDeviceToHost, s.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "device->host bits copy");
+        if (e != cudaSuccess) return drain_and_return(c, cuda_fail(e, "device->host bits copy"));
     }
     return sync_all(c);
 }
@@ -1231,9 +1243,14 @@ int svs_embed_frames_host(svs_ctx* c, const uint8_t* h_frames, int channels, int
         const long long byte0 = (payload_bit_offset >> 5) << 2;
         const long long byte1 = (payload_bit_offset + usable + 7) >> 3;
         dev_bit_offset = payload_bit_offset - 8 * byte0;
-        if (int rc = ensure(c->payload, c->payload_cap, (size_t)(byte1 - byte0 + 4))) return rc;
-        cudaError_t e = cudaMemcpyAsync(c->payload, h_payload + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice, c->slot[0].stream);
-        if (e != cudaSuccess) return cuda_fail(e, "host->device payload copy");
+        // the kernels read whole 32-bit words, up to two words past the one that holds a block's
+        // first bit (masked by payload_last_word, which svs_embed_frames derives from the bit count):
+        // 12 zeroed bytes of slack keep every such read inside the allocation
+        if (int rc = ensure(c->payload, c->payload_cap, (size_t)(byte1 - byte0 + 12))) return rc;
+        cudaError_t e = cudaMemsetAsync(c->payload + (byte1 - byte0), 0, 12, c->slot[0].stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->payload, h_payload + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice, c->slot[0].stream);
+        if (e != cudaSuccess) return drain_and_return(c, cuda_fail(e, "host->device payload copy"));
         cudaEventRecord(c->payload_ready, c->slot[0].stream);
         cudaStreamWaitEvent(c->slot[1].stream, c->payload_ready, 0);
         cudaStreamWaitEvent(c->slot[2].stream, c->payload_ready, 0);
@@ -1244,26 +1261,26 @@ int svs_embed_frames_host(svs_ctx* c, const uint8_t* h_frames, int channels, int
     for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
         svs_slot& s = c->slot[k % 3];
         const long long nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        if (int rc = ensure(s.buf[0], s.cap[0], (size_t)(nf * in_bytes))) return rc;
-        if (int rc = ensure(s.buf[1], s.cap[1], (size_t)(nf * out_bytes))) return rc;
-        if (h_gray_out) if (int rc = ensure(s.buf[2], s.cap[2], (size_t)(nf * px))) return rc;
-        if (int rc = ensure(s.buf[3], s.cap[3], (size_t)(nf * 16))) return rc;
+        if (int rc = ensure(s.buf[0], s.cap[0], (size_t)(nf * in_bytes))) return drain_and_return(c, rc);
+        if (int rc = ensure(s.buf[1], s.cap[1], (size_t)(nf * out_bytes))) return drain_and_return(c, rc);
+        if (h_gray_out) if (int rc = ensure(s.buf[2], s.cap[2], (size_t)(nf * px))) return drain_and_return(c, rc);
+        if (int rc = ensure(s.buf[3], s.cap[3], (size_t)(nf * 16))) return drain_and_return(c, rc);
         int64_t* d_nbits = reinterpret_cast<int64_t*>(s.buf[3]);
         unsigned long long* d_sse = reinterpret_cast<unsigned long long*>(s.buf[3] + nf * 8);
         cudaError_t e = copy_frames_in(s.buf[0], h_frames + f0 * frame_stride, nf, height, row_bytes, frame_stride, row_stride, s.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "host->device frame copy");
+        if (e != cudaSuccess) return drain_and_return(c, cuda_fail(e, "host->device frame copy"));
         if (h_sse_out) cudaMemsetAsync(d_sse, 0, (size_t)(nf * 8), s.stream);
         const long long first = active ? f0 * cap : 0;            // payload bits consumed by earlier chunks
         if (int rc = svs_embed_frames(s.buf[0], channels, nf, height, width, in_bytes, row_bytes,
                                       c->payload, dev_bit_offset + first, payload_total_bits - first, delta, num_ac,
                                       s.buf[1], stego_channels, out_bytes, (long long)width * stego_channels,
                                       h_gray_out ? s.buf[2] : nullptr, h_bits_embedded_out ? d_nbits : nullptr,
-                                      h_sse_out ? d_sse : nullptr, s.stream)) return rc;
+                                      h_sse_out ? d_sse : nullptr, s.stream)) return drain_and_return(c, rc);
         e = cudaMemcpyAsync(h_stego_out + f0 * out_bytes, s.buf[1], (size_t)(nf * out_bytes), cudaMemcpyDeviceToHost, s.stream);
         if (e == cudaSuccess && h_gray_out) e = cudaMemcpyAsync(h_gray_out + f0 * px, s.buf[2], (size_t)(nf * px), cudaMemcpyDeviceToHost, s.stream);
         if (e == cudaSuccess && h_bits_embedded_out) e = cudaMemcpyAsync(h_bits_embedded_out + f0, d_nbits, (size_t)(nf * 8), cudaMemcpyDeviceToHost, s.stream);
         if (e == cudaSuccess && h_sse_out) e = cudaMemcpyAsync(h_sse_out + f0, d_sse, (size_t)(nf * 8), cudaMemcpyDeviceToHost, s.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "device->host result copy");
+        if (e != cudaSuccess) return drain_and_return(c, cuda_fail(e, "device->host result copy"));
     }
     return sync_all(c);
 }

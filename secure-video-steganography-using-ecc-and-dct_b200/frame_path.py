@@ -216,6 +216,14 @@ def embed_frames(frames, payload, total_bits, delta, num_ac=63, *, bit_offset=0,
     else:
         if not (payload.is_cuda and payload.dtype == torch.uint8 and payload.is_contiguous()):
             raise TypeError("payload must be a contiguous CUDA uint8 tensor (packed bits)")
+        if payload.numel() * 8 < int(bit_offset) + int(total_bits):
+            raise ValueError("payload holds %d bits, bit_offset + total_bits = %d"
+                             % (payload.numel() * 8, int(bit_offset) + int(total_bits)))
+        if payload.numel() % 4 or payload.data_ptr() % 4:
+            # the kernels read whole 32-bit words (include/svs_b200.h): give them a padded, aligned copy
+            padded = torch.zeros((payload.numel() + 3) // 4 * 4, dtype=torch.uint8, device=payload.device)
+            padded[:payload.numel()] = payload
+            payload = padded
         pay_ptr = payload.data_ptr()
     with torch.cuda.device(dev):
         rc = _native.lib().svs_embed_frames(

@@ -141,6 +141,28 @@ def test_batched_embed_extract_match_oracle(shape, delta, n, frac, kernel_family
     assert np.array_equal(want, ext.cpu().numpy()), "extract(cover) differs"
 
 
+def test_narrow_frames_and_unpadded_payloads(kernel_family):
+    """W = 8 (one block per block row: every division helper degenerates) and W = 24, with a
+    payload whose byte length is not a multiple of 4 (embed_frames pads it) and a payload that
+    is too short for the bits announced (rejected before any launch)."""
+    for shape in ((3, 40, 8, 3), (2, 16, 24)):
+        frames = synth_frames("narrow%s" % (shape,), shape)
+        nf, h, w = shape[:3]
+        n, delta = 63, 20
+        cap = svs_b200.capacity_bits(h, w, n)
+        total = nf * cap - 13
+        bits = synth_bits("narrow", total)
+        packed = np.packbits(bits)
+        res = svs_b200.embed_frames(_dev(frames), _dev(packed), total, delta, n, want_bits_embedded=True)
+        stego, _, nb = oc.embed_frames(frames, packed, total, delta, n)
+        _assert_same_pixels(stego, res.stego.cpu().numpy(), "stego %s" % (shape,))
+        assert np.array_equal(nb, res.bits_embedded.cpu().numpy())
+        ext = svs_b200.extract_frames(res.stego, delta, n)
+        assert np.array_equal(oc.extract_frames(stego, delta, n), ext.cpu().numpy())
+        with pytest.raises(ValueError):
+            svs_b200.embed_frames(_dev(frames), _dev(packed[:-1]), total, delta, n)
+
+
 def test_payload_bit_offset_and_tail_frames():
     frames = synth_frames("off", (6, 64, 96, 3))
     n, delta = 63, 20
