@@ -2,7 +2,7 @@
 """Throughput of the N2 variants: embed with the fused GRAY2BGR store, extract from a
 3-channel stego (what the receiver decodes from the FFV1 file), with the fused SSE (N3) - next to
 the headline gray-stego path.  600 x 1080p frames, 63 AC, delta 20, CUDA events, best of 3.
-Usage: python profiles/n2_throughput.py > profiles/r1_n2_throughput.txt   (GPU box)"""
+Usage: python profiles/n2_throughput.py > profiles/r2_n2_throughput.txt   (GPU box)"""
 import os
 import sys
 
@@ -38,7 +38,7 @@ px = H * W
 rows = [
     ("embed BGR -> gray stego (headline)", lambda: svs_b200.embed_frames(frames, payload, F * cap, D, N, out=gray_out), 4 * px + cap // 8),
     ("embed BGR -> BGR stego (N2: fused GRAY2BGR)", lambda: svs_b200.embed_frames(frames, payload, F * cap, D, N, stego_channels=3, out=bgr_out), 6 * px + cap // 8),
-    ("embed BGR -> gray stego + per-frame SSE (N3: + streaming kernel)", lambda: svs_b200.embed_frames(frames, payload, F * cap, D, N, out=gray_out, want_sse=True), 4 * px + cap // 8),
+    ("embed BGR -> gray stego + per-frame SSE (N3: fused epilogue)", lambda: svs_b200.embed_frames(frames, payload, F * cap, D, N, out=gray_out, want_sse=True), 4 * px + cap // 8),
     ("extract gray stego (headline)", lambda: svs_b200.extract_frames(gray_out, D, N, out=bits), px + cap // 8),
     ("extract BGR stego (N2: what the FFV1 reader delivers)", lambda: svs_b200.extract_frames(bgr_out, D, N, out=bits), 3 * px + cap // 8),
 ]

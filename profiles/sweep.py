@@ -7,7 +7,7 @@
   config 4: 3840x2160 frames, 63 and 10 AC, embed + extract round trip (75 frames = one GPU's share of
             the 600-frame batch on 8 GPUs).
 
-Usage: python profiles/sweep.py > profiles/r1_sweep.jsonl     (GPU box; prints one JSON object per point)
+Usage: python profiles/sweep.py > profiles/r2_sweep.jsonl     (GPU box; prints one JSON object per point)
 """
 import json
 import os

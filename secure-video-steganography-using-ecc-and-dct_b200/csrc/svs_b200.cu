@@ -598,7 +598,7 @@ cudaError_t blk_smem_optin(const void* kernel, int bytes, bool (&ready)[64])
 template <int CH, int OC, bool NFULL, bool SIDE>
 cudaError_t launch_blk_embed_one(const blk::BlkEmbedArgs& ba, cudaStream_t st)
 {
-    constexpr int smem = blk::blk_smem_bytes<CH, true>();
+    constexpr int smem = blk::blk_embed_smem_bytes<CH, SIDE>();
     static bool ready[64] = {false};
     if (cudaError_t e = blk_smem_optin(reinterpret_cast<const void*>(blk::embed_blk_kernel<CH, OC, NFULL, SIDE>), smem, ready)) return e;
     blk::embed_blk_kernel<CH, OC, NFULL, SIDE><<<blk_grid(ba.g.total_groups), blk::kBlkThreads, smem, st>>>(ba);

@@ -567,6 +567,10 @@ constexpr bool blk_uses_smem() { return kBlkStage == 2; }
 // dynamic shared memory of a kernel instantiation: the cp.async slots, 8 bytes x rows x words x threads
 template <int CH, bool EMBED>
 constexpr int blk_smem_bytes() { return blk_uses_smem<CH, EMBED>() ? 8 * (CH == 3 ? 3 : 1) * 8 * kBlkThreads : 0; }
+// SIDE embed kernels park the block's 16 gray words in shared memory between the input stage and
+// the epilogue (16 registers the transforms need): word k of thread t at (k * kBlkThreads + t) * 4
+template <int CH, bool SIDE>
+constexpr int blk_embed_smem_bytes() { return blk_smem_bytes<CH, true>() + (SIDE ? 16 * 4 * kBlkThreads : 0); }
 
 // A warp owns 32 consecutive blocks of a frame in raster order ("group"): BGR rows arrive as
 // three 8-byte accesses per lane over one 768-byte contiguous span, stego rows leave as
@@ -763,8 +767,23 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
         }
         if (w.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[w.f] = a.cap;
         P2 c[32];
-        uint32_t stego[16], gray[16];
-        block_input<CH, SIDE>(rows, G.magic_hi, c, gray);
+        uint32_t stego[16];
+        uint32_t* const park = reinterpret_cast<uint32_t*>(blk_dyn_smem + blk_smem_bytes<CH, true>()) + threadIdx.x;
+        {
+            uint32_t gray[16];
+            block_input<CH, SIDE>(rows, G.magic_hi, c, gray);
+            if (SIDE) {
+                if (a.gray != nullptr && w.ok) {
+                    uint8_t* gd = a.gray + w.f * a.gray_frame_stride + (long long)(w.by * 8) * a.W + w.bx * 8;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) stg64(gd + (long long)r * a.W, gray[2 * r], gray[2 * r + 1]);
+                }
+                if (a.sse != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) park[k * kBlkThreads] = gray[k];
+                }
+            }
+        }
         uint32_t w0, w1;
         payload_window(pw, w0, w1);
 
@@ -793,16 +812,11 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
             }
         }
         if (SIDE) {
-            if (a.gray != nullptr && w.ok) {
-                uint8_t* gd = a.gray + w.f * a.gray_frame_stride + (long long)(w.by * 8) * a.W + w.bx * 8;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) stg64(gd + (long long)r * a.W, gray[2 * r], gray[2 * r + 1]);
-            }
             if (a.sse != nullptr) {
                 uint32_t sq = 0;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const uint32_t d = hw::absdiff4(gray[k], stego[k]);
+                    const uint32_t d = hw::absdiff4(park[k * kBlkThreads], stego[k]);
                     sq = hw::dp4a(d, d, sq);                                 // <= 64 * 255^2 per block
                 }
                 if (!w.ok) sq = 0;

@@ -45,7 +45,13 @@ HEADER_BITS = 976        # everything before the ciphertext for P-256 / 16-byte 
 # compute back-ends (GPU by default)
 # ----------------------------------------------------------------------------------------------
 class GpuFrameOps:
-    """Batched embed / extract on one CUDA device; the packed payload is uploaded once."""
+    """Batched embed / extract on one CUDA device.
+
+    The packed payload is uploaded once; frames travel through reusable PINNED host buffers
+    (asynchronous H2D / D2H on the device's copy engines, no pageable staging copies inside the
+    driver), and the results are handed back as views of pinned memory that stay valid until the
+    next call of the same kind - the caller (the writer thread of `embed_frame_stream`) consumes
+    them before that."""
 
     def __init__(self, device=None):
         import torch
@@ -55,6 +61,7 @@ class GpuFrameOps:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._payload = None
         self._payload_src = None
+        self._pinned = {}
 
     def _device_payload(self, packed):
         if self._payload_src is not packed:
@@ -64,20 +71,38 @@ class GpuFrameOps:
             self._payload_src = packed
         return self._payload
 
+    def _pin(self, key, shape):
+        """A pinned uint8 buffer of at least `shape` (grown geometrically, reused across batches)."""
+        n = int(np.prod(shape))
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < n:
+            buf = self.torch.empty(max(n, 2 * (buf.numel() if buf is not None else 0)), dtype=self.torch.uint8).pin_memory()
+            self._pinned[key] = buf
+        return buf[:n].view(*shape)
+
+    def _upload(self, frames):
+        frames = np.asarray(frames)
+        stage = self._pin("in", frames.shape)
+        stage.numpy()[...] = frames                            # one host copy into pinned memory
+        return stage.to(self.device, non_blocking=True)
+
     def embed(self, frames, packed, bit_offset, nbits, delta, num_ac, want_gray):
         """frames (k,h,w,3|none) u8 -> (stego_bgr (k,h,w,3), gray of frame 0 or None, bits per frame)."""
         t = self.torch
-        d = t.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
+        d = self._upload(frames)
         res = frame_path.embed_frames(d, self._device_payload(packed), int(nbits), delta, num_ac,
                                       bit_offset=int(bit_offset), stego_channels=3, want_gray=bool(want_gray),
                                       want_bits_embedded=True)
+        out = self._pin("stego", tuple(res.stego.shape))
+        out.copy_(res.stego, non_blocking=True)
         gray0 = res.gray[0].cpu().numpy() if want_gray else None
-        return res.stego.cpu().numpy(), gray0, res.bits_embedded.cpu().numpy()
+        nb = res.bits_embedded.cpu().numpy()                   # synchronises the stream: `out` is complete
+        t.cuda.current_stream(self.device).synchronize()
+        return out.numpy(), gray0, nb
 
     def extract(self, frames, delta, num_ac):
         """frames (k,h,w[,3]) u8 -> (k, ceil(cap/8)) packed bits."""
-        t = self.torch
-        d = t.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
+        d = self._upload(frames)
         return frame_path.extract_frames(d, delta, num_ac).cpu().numpy()
 
 
@@ -94,12 +119,88 @@ def _ops():
 # ----------------------------------------------------------------------------------------------
 # embed: the frame loop of embed_process.py:108-144
 # ----------------------------------------------------------------------------------------------
+class _Prefetch:
+    """Decode ahead on a worker thread: batches of up to `n` frames (cv2 releases the GIL while it
+    decodes, so this overlaps the GPU call and the encoder)."""
+
+    def __init__(self, read_frame, n, crop, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=depth)
+        self.err = None
+
+        def work():
+            try:
+                while True:
+                    batch = []
+                    while len(batch) < n:
+                        ok, frame = read_frame()
+                        if not ok:
+                            break
+                        batch.append(crop(frame))
+                    self.q.put(batch)
+                    if len(batch) < n:
+                        if batch:
+                            self.q.put([])
+                        return
+            except BaseException as exc:            # surfaced on the consumer side
+                self.err = exc
+                self.q.put([])
+
+        self.t = threading.Thread(target=work, daemon=True)
+        self.t.start()
+
+    def next(self):
+        batch = self.q.get()
+        if self.err is not None:
+            raise self.err
+        return batch
+
+
+class _Writer:
+    """Encode behind on a worker thread (FFV1 encoding is the slowest stage of the pipeline)."""
+
+    def __init__(self, write_frame, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=depth)
+        self.err = None
+
+        def work():
+            while True:
+                frames = self.q.get()
+                if frames is None:
+                    return
+                try:
+                    if self.err is None:
+                        for f in frames:
+                            write_frame(f)
+                except BaseException as exc:
+                    self.err = exc
+
+        self.t = threading.Thread(target=work, daemon=True)
+        self.t.start()
+
+    def put(self, frames):
+        if self.err is not None:
+            raise self.err
+        self.q.put(frames)
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+        if self.err is not None:
+            raise self.err
+
+
 def embed_frame_stream(read_frame, write_frame, payload_packed, total_bits, delta, num_ac, out_hw, *,
-                       batch_frames=32, embed_fn=None, log=None):
+                       batch_frames=32, embed_fn=None, log=None, overlap_io=True):
     """Embed `total_bits` of `payload_packed` (MSB-first) into the frames `read_frame()` yields.
 
     read_frame()  -> (ok, frame_bgr) like cv2.VideoCapture.read; frames are cropped to out_hw
     write_frame(a)   receives one (h,w,3) uint8 BGR frame, like cv2.VideoWriter.write
+    overlap_io       decode the next batch and encode the previous one on worker threads while the
+                     current one is on the GPU (same frames, same order; False = strictly serial)
     Returns (all_embedded, first_gray, first_stego_gray, frames_seen): what the reference's
     loop leaves behind (embed_process.py:147-152).
     """
@@ -115,32 +216,52 @@ def embed_frame_stream(read_frame, write_frame, payload_packed, total_bits, delt
     first_gray = first_stego = None
     embedded = 0
     done = False
-    while True:
-        batch = []
-        while len(batch) < batch_frames:
-            ok, frame = read_frame()
-            if not ok:
+    crop = lambda frame: frame[0:h, 0:w]
+    if overlap_io:
+        source, sink = _Prefetch(read_frame, batch_frames, crop), _Writer(write_frame)
+        next_batch, emit = source.next, sink.put
+    else:
+        def next_batch():
+            batch = []
+            while len(batch) < batch_frames:
+                ok, frame = read_frame()
+                if not ok:
+                    break
+                batch.append(crop(frame))
+            return batch
+
+        def emit(frames):
+            for f in frames:
+                write_frame(f)
+    try:
+        while True:
+            batch = next_batch()
+            if not batch:
                 break
-            batch.append(frame[0:h, 0:w])
-        if not batch:
-            break
-        k = 0 if total_bits == 0 else int(min(len(batch), max(0, n_embed - seen)))
-        if k:
-            stack = np.stack([np.asarray(f) for f in batch[:k]])
-            off = seen * cap
-            stego, gray0, nbits = embed_fn(stack, payload_packed, off, total_bits - off, delta, num_ac, seen == 0)
-            if seen == 0:
-                first_gray, first_stego = gray0, np.ascontiguousarray(stego[0, :, :, 0])
-            for i in range(k):
-                write_frame(stego[i])
-                embedded += int(nbits[i])
-                log("    Frame %d: %d bits disisipkan. Total disisipkan: %d/%d" % (seen + i + 1, int(nbits[i]), embedded, total_bits))
-            if embedded >= total_bits:
-                done = True
-        for f in batch[k:]:                                   # past the payload: copied in colour (:131-140)
-            f = np.asarray(f)
-            write_frame(f if f.ndim == 3 else np.repeat(f[..., None], 3, 2))
-        seen += len(batch)
+            k = 0 if total_bits == 0 else int(min(len(batch), max(0, n_embed - seen)))
+            if k:
+                stack = np.stack([np.asarray(f) for f in batch[:k]])
+                off = seen * cap
+                stego, gray0, nbits = embed_fn(stack, payload_packed, off, total_bits - off, delta, num_ac, seen == 0)
+                if seen == 0:
+                    first_gray, first_stego = gray0, np.ascontiguousarray(stego[0, :, :, 0])
+                # (the stego batch may live in a reused pinned buffer: hand the writer its own copy)
+                emit([np.array(stego[i]) for i in range(k)] if overlap_io else [stego[i] for i in range(k)])
+                for i in range(k):
+                    embedded += int(nbits[i])
+                    log("    Frame %d: %d bits disisipkan. Total disisipkan: %d/%d" % (seen + i + 1, int(nbits[i]), embedded, total_bits))
+                if embedded >= total_bits:
+                    done = True
+            rest = []
+            for f in batch[k:]:                               # past the payload: copied in colour (:131-140)
+                f = np.asarray(f)
+                rest.append(f if f.ndim == 3 else np.repeat(f[..., None], 3, 2))
+            if rest:
+                emit(rest)
+            seen += len(batch)
+    finally:
+        if overlap_io:
+            sink.close()
     if not done:
         log("    Warning: Video selesai sebelum semua payload (%d bits) disisipkan." % total_bits)
         return False, None, None, seen
@@ -151,7 +272,12 @@ def embed_frame_stream(read_frame, write_frame, payload_packed, total_bits, delt
 # extract: the read-as-needed loops of extract_process.py:55-86 and :173-182
 # ----------------------------------------------------------------------------------------------
 class StegoBitReader:
-    """The extracted bit stream of a stego video, served in payload order by whole bytes."""
+    """The extracted bit stream of a stego video, served in payload order by whole bytes.
+
+    The stream is kept PACKED (one bytearray + a bit cursor), never as one byte or character per
+    bit: appending a batch and taking a field both cost time proportional to what is appended /
+    taken, not to what has accumulated (the reference re-concatenates an ever growing string,
+    extract_process.py:76,181)."""
 
     def __init__(self, read_frame, delta, num_ac, out_hw, *, batch_frames=8, extract_fn=None, log=None):
         self.read_frame = read_frame
@@ -161,13 +287,30 @@ class StegoBitReader:
         self.extract_fn = extract_fn or _ops().extract
         self.log = log or (lambda *_: None)
         self.cap = frame_path.capacity_bits(self.h, self.w, num_ac)
-        self.bits = np.zeros(0, np.uint8)                     # unread bits (0/1), head at self.pos
-        self.pos = 0
+        self.buf = bytearray()                                # packed MSB-first; self.end valid bits
+        self.end = 0
+        self.pos = 0                                          # bit cursor
         self.frames_read = 0
         self.exhausted = False
 
     def available(self):
-        return self.bits.size - self.pos
+        return self.end - self.pos
+
+    def _append_rows(self, packed):
+        """Append `cap` bits of every row of `packed` (k, ceil(cap/8)) to the stream."""
+        packed = np.asarray(packed, np.uint8)
+        if self.cap % 8 == 0 and self.end % 8 == 0:           # every BASELINE geometry: plain byte append
+            self.buf += packed[:, :self.cap // 8].tobytes()
+            self.end += packed.shape[0] * self.cap
+            return
+        # general case: merge at bit granularity, touching only the partial tail byte and the new rows
+        tail_bits = self.end % 8
+        head = np.unpackbits(np.frombuffer(bytes(self.buf[-1:]), np.uint8))[:tail_bits] if tail_bits else np.zeros(0, np.uint8)
+        fresh = np.unpackbits(packed, axis=1)[:, :self.cap].reshape(-1)
+        if tail_bits:
+            del self.buf[-1:]
+        self.buf += np.packbits(np.concatenate([head, fresh])).tobytes()
+        self.end += fresh.size
 
     def ensure(self, nbits):
         """Make at least `nbits` unread bits available; False if the video ends first."""
@@ -185,10 +328,7 @@ class StegoBitReader:
                 break
             if self.cap == 0:
                 raise ValueError("no bits can be extracted (num_ac <= 0)")
-            packed = self.extract_fn(np.stack(frames), self.delta, self.num_ac)
-            fresh = np.unpackbits(np.asarray(packed, np.uint8), axis=1)[:, :self.cap].reshape(-1)
-            self.bits = np.concatenate([self.bits[self.pos:], fresh])
-            self.pos = 0
+            self._append_rows(self.extract_fn(np.stack(frames), self.delta, self.num_ac))
             self.frames_read += len(frames)
             self.log("    %d frame diekstrak (total %d), %d bit tersedia" % (len(frames), self.frames_read, self.available()))
         return self.available() >= nbits
@@ -196,7 +336,12 @@ class StegoBitReader:
     def take_bytes(self, n):
         if not self.ensure(8 * n):
             raise EOFError("video ended before %d more bytes could be extracted" % n)
-        out = np.packbits(self.bits[self.pos:self.pos + 8 * n]).tobytes()
+        first, shift = self.pos >> 3, self.pos & 7
+        if shift == 0:
+            out = bytes(self.buf[first:first + n])
+        else:                                                 # unaligned cursor: shift the window only
+            window = np.frombuffer(bytes(self.buf[first:first + n + 1]), np.uint8)
+            out = np.packbits(np.unpackbits(window)[shift:shift + 8 * n]).tobytes()
         self.pos += 8 * n
         return out
 

@@ -84,6 +84,9 @@ def build_cases():
     add("bgr_480x640_d20_ac63", synth_frames("cfg2b", (480, 640, 3)), 20, 63, full=False)
     add("bgr_1080p_d20_ac63_fullrange", synth_frames("cfg3", (1080, 1920, 3)), 20, 63, full=False)
     add("bgr_1080p_d20_ac10_midrange", synth_frames("cfg3m", (1080, 1920, 3), 64, 192), 20, 10, full=False)
+    # round 2: BASELINE config 4 (3840x2160); generated with `make_golden.py --append <names>`
+    add("bgr_4k_d20_ac63_midrange", synth_frames("cfg4", (2160, 3840, 3), 64, 192), 20, 63, full=False)
+    add("bgr_4k_d20_ac10_fullrange", synth_frames("cfg4f", (2160, 3840, 3)), 20, 10, full=False)
     return cases
 
 
@@ -150,7 +153,25 @@ def make_e2e():
     print("e2e payload: %d bits for %dx%d image" % (bits.size, w, h))
 
 
+def append(names):
+    """Run only the named digest-only cases and merge them into cases.json (the existing fixtures -
+    in particular the randomly keyed e2e payload - stay untouched)."""
+    with open(os.path.join(HERE, "cases.json")) as f:
+        doc = json.load(f)
+    have = {c["name"] for c in doc["cases"]}
+    for c in build_cases():
+        if c["name"] in names and c["name"] not in have:
+            assert not c["full"], "--append is for digest-only cases"
+            m, _ = run_case(c)
+            doc["cases"].append(m)
+            print("%-36s emb=%-8d ext=%-8d %.2fs" % (m["name"], m["bits_embedded"], m["n_extracted"], m["ref_seconds"]))
+    with open(os.path.join(HERE, "cases.json"), "w") as f:
+        json.dump(doc, f, indent=1)
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--append":
+        return append(set(sys.argv[2:]))
     metas, arrays = [], {}
     for c in build_cases():
         m, a = run_case(c)

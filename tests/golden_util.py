@@ -21,6 +21,8 @@ _BIG_INPUTS = {
     "bgr_480x640_d20_ac63": lambda: synth_frames("cfg2b", (480, 640, 3)),
     "bgr_1080p_d20_ac63_fullrange": lambda: synth_frames("cfg3", (1080, 1920, 3)),
     "bgr_1080p_d20_ac10_midrange": lambda: synth_frames("cfg3m", (1080, 1920, 3), 64, 192),
+    "bgr_4k_d20_ac63_midrange": lambda: synth_frames("cfg4", (2160, 3840, 3), 64, 192),
+    "bgr_4k_d20_ac10_fullrange": lambda: synth_frames("cfg4f", (2160, 3840, 3)),
 }
 
 

@@ -93,6 +93,19 @@ def test_loop_port_against_golden(name):
     G.check_extract(c, np.frombuffer(s.encode(), np.uint8) - 48, "ext_stego")
 
 
+def test_loop_port_against_the_480p_digest_case():
+    """The loop port at a full 640x480 frame (BASELINE config 2 shape): what bench.py times as the
+    CPU baseline when no staged reference is present must itself be pinned at a realistic size."""
+    pytest.importorskip("scipy.fftpack")
+    from oracle import ref_port
+    c, frame, bits = G.get_case("bgr_480x640_d20_ac10_cfg2")
+    gray, stego, n = ref_port.proses_frame_qim_dct(frame, 'embed', c["delta"], bits_to_str(bits),
+                                                   num_ac_coeffs_to_use=c["num_ac"])
+    G.check_embed(c, gray, stego, n)
+    s = ref_port.proses_frame_qim_dct(stego, 'extract', c["delta"], num_ac_coeffs_to_use=c["num_ac"])
+    G.check_extract(c, np.frombuffer(s.encode(), np.uint8) - 48, "ext_stego")
+
+
 def test_c_oracle_batch_offsets_and_threads():
     """Frame f consumes payload bits [f*cap, (f+1)*cap) (embed_process.py:115-128)."""
     frames = synth_frames("batch", (5, 32, 40, 3))

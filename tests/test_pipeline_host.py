@@ -112,6 +112,38 @@ def test_bit_reader_reads_only_what_it_needs():
         rd.take_bytes(2)
 
 
+def test_bit_reader_with_frames_that_do_not_end_on_a_byte():
+    """cap % 8 != 0: rows are merged at bit granularity, the cursor may sit inside a byte."""
+    h, w, n, delta = 24, 40, 7, 20                                   # 15 blocks x 7 = 105 bits per frame
+    frames = synth_frames("reader2", (11, h, w))
+    cap = svs_b200.capacity_bits(h, w, n)
+    assert cap % 8 == 1
+    stream = np.concatenate([np.unpackbits(r)[:cap] for r in oc.extract_frames(frames, delta, n)])
+    feed = Feed(frames)
+    rd = pipeline.StegoBitReader(feed.read, delta, n, (h, w), batch_frames=3, extract_fn=oracle_extract)
+    pos = 0
+    for nbytes in (1, 13, 2, 40, 5, 60):
+        assert rd.take_bytes(nbytes) == np.packbits(stream[pos:pos + 8 * nbytes]).tobytes()
+        pos += 8 * nbytes
+    assert rd.available() == rd.frames_read * cap - pos and rd.frames_read <= 11
+
+
+def test_embed_stream_with_and_without_io_threads_write_the_same_frames():
+    h, w, n, delta = 40, 56, 17, 12
+    frames = synth_frames("pipe-threads", (9, 43, 59, 3), 40, 220)
+    cap = svs_b200.capacity_bits(h, w, n)
+    bits = synth_bits("pipe-threads", int(3.3 * cap))
+    outs = []
+    for overlap in (False, True):
+        written = []
+        res = pipeline.embed_frame_stream(Feed(frames).read, lambda a: written.append(np.array(a)), np.packbits(bits),
+                                          bits.size, delta, n, (h, w), batch_frames=2, embed_fn=oracle_embed,
+                                          overlap_io=overlap)
+        outs.append((res[0], res[3], written))
+    assert outs[0][0] is True and outs[0][:2] == outs[1][:2] and len(outs[0][2]) == 9
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))
+
+
 def test_payload_layout_round_trip_and_golden():
     """build_payload reproduces the payload the reference built for image64.png (tests/golden)."""
     from tests import golden_util as G
