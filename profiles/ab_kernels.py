@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--w", type=int, default=1920)
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--sse", action="store_true", help="embed with the fused per-frame SSE output (SIDE kernels)")
     ap.add_argument("--lib", default="", help="another build of libsvs_b200.so (e.g. variants/libsvs_variants.so)")
     a = ap.parse_args()
     if a.lib:
@@ -49,7 +50,7 @@ def main():
             for it in range(3 + a.iters):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
-                res = svs_b200.embed_frames(frames, payload, total, a.delta, n)
+                res = svs_b200.embed_frames(frames, payload, total, a.delta, n, want_sse=a.sse)
                 e1.record()
                 bits = svs_b200.extract_frames(res.stego, a.delta, n)
                 e2.record()
