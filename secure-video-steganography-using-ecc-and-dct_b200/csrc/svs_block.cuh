@@ -260,25 +260,31 @@ SVS_HD uint32_t window_bit(uint32_t w0, uint32_t w1, int idx) { return ((idx < 3
 // space.  `orig` holds the 8 coefficient pairs of rows 2i / 2i+1 before quantisation, `res`
 // the results of the division-free quantiser; every coefficient whose fraction was too close
 // to a rounding boundary is recomputed as the scalar kernels do (IEEE division, round-half-
-// even, float32 product) and patched into `res`.
+// even, float32 product) and patched into `res`.  Scalars only (an array indexed by the lane
+// would live in local memory): a call costs 8 loads of `orig` and touches `res` only where a
+// coefficient is actually flagged.
 SVS_RARE void fix_pair_embed(const P2* orig, P2* res, int i, int n, float d, float r, float r2, float ke, uint32_t emask,
                     uint32_t w0, uint32_t w1)
 {
 #pragma unroll 1
     for (int v = 0; v < 8; ++v) {
-        float c[2], o[2];
-        hw::unpkf(orig[v], c[0], c[1]);
-        hw::unpkf(res[v], o[0], o[1]);
-#pragma unroll 1
-        for (int l = 0; l < 2; ++l) {
-            const int idx = 16 * i + 8 * l + v - 1;
-            if (idx < 0 || idx >= n) continue;
-            if ((hw::f2u(hw::ffma(c[l], r2, ke)) & emask) < kZone) {
-                const int q = hw::f2i_rn(div_exact(c[l], d, r));
-                o[l] = hw::fmul(hw::i2f(q - (q & 1) + (int)window_bit(w0, w1, idx)), d);
-            }
+        float ca, cb;
+        hw::unpkf(orig[v], ca, cb);
+        const int ia = 16 * i + v - 1, ib = ia + 8;
+        const bool fa = ia >= 0 && ia < n && (hw::f2u(hw::ffma(ca, r2, ke)) & emask) < kZone;
+        const bool fb = ib < n && (hw::f2u(hw::ffma(cb, r2, ke)) & emask) < kZone;
+        if (!(fa || fb)) continue;
+        float oa, ob;
+        hw::unpkf(res[v], oa, ob);
+        if (fa) {
+            const int q = hw::f2i_rn(div_exact(ca, d, r));
+            oa = hw::fmul(hw::i2f(q - (q & 1) + (int)window_bit(w0, w1, ia)), d);
         }
-        res[v] = hw::pk(o[0], o[1]);
+        if (fb) {
+            const int q = hw::f2i_rn(div_exact(cb, d, r));
+            ob = hw::fmul(hw::i2f(q - (q & 1) + (int)window_bit(w0, w1, ib)), d);
+        }
+        res[v] = hw::pk(oa, ob);
     }
 }
 
@@ -288,17 +294,16 @@ SVS_RARE uint32_t fix_pair_extract(const P2* in, uint32_t rows, int i, int n, fl
 {
 #pragma unroll 1
     for (int v = 0; v < 8; ++v) {
-        float c[2];
-        hw::unpkf(in[v], c[0], c[1]);
-#pragma unroll 1
-        for (int l = 0; l < 2; ++l) {
-            const int idx = 16 * i + 8 * l + v - 1;
-            if (idx < 0 || idx >= n) continue;
-            if ((hw::f2u(hw::ffma(c[l], r, kx)) & xmask) < kZone) {
-                const uint32_t par = (uint32_t)hw::f2i_rn(div_exact(c[l], d, r)) & 1u;
-                const int at = 16 * l + 7 - v;
-                rows = (rows & ~(1u << at)) | (par << at);
-            }
+        float ca, cb;
+        hw::unpkf(in[v], ca, cb);
+        const int ia = 16 * i + v - 1, ib = ia + 8;
+        if (ia >= 0 && ia < n && (hw::f2u(hw::ffma(ca, r, kx)) & xmask) < kZone) {
+            const uint32_t par = (uint32_t)hw::f2i_rn(div_exact(ca, d, r)) & 1u;
+            rows = (rows & ~(0x80u >> v)) | (par << (7 - v));
+        }
+        if (ib < n && (hw::f2u(hw::ffma(cb, r, kx)) & xmask) < kZone) {
+            const uint32_t par = (uint32_t)hw::f2i_rn(div_exact(cb, d, r)) & 1u;
+            rows = (rows & ~(0x800000u >> v)) | (par << (23 - v));
         }
     }
     return rows;
