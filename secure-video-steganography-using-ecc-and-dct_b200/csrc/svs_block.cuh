@@ -88,7 +88,13 @@ SVS_HD uint32_t magic_byte(uint32_t v, uint32_t magic_hi, int sel) { return hw::
 // weights are placed according to where the pixel's three bytes sit in the words (no shuffles).
 SVS_HD void bgr_row_sums(const uint32_t (&v)[6], uint32_t (&s)[8])
 {
-    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
+// SVS_BLK_PRMT1 (experiment, OFF): the rounding constant also carries 0x4B in the top byte and one
+// single-register PRMT makes the float (bgr_sum_to_float) - no magic-constant register, 35 MOVs
+// fewer per group.  MEASURED: slower (embed 1.613 vs 1.571 ms per 600 frames).
+#ifndef SVS_BLK_PRMT1
+#define SVS_BLK_PRMT1 0
+#endif
+    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u + (SVS_BLK_PRMT1 ? 0x4B000000u : 0u);
 #pragma unroll
     for (int px = 0; px < 8; ++px) {
         const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
@@ -98,6 +104,10 @@ SVS_HD void bgr_row_sums(const uint32_t (&v)[6], uint32_t (&s)[8])
         else               s[px] = hw::dp2a_lo((WR << 16) | WG, v[wi + 1], hw::dp2a_hi(WB << 16, v[wi], RND));
     }
 }
+
+// s = 0x4B | gray | 16 fraction bits  ->  bits of the float 2^23 + 256 * gray = [0x00, gray, 0x00, 0x4B]:
+// byte 3 as is, byte 2 to byte 1, and the two zero bytes as sign replication of byte 3 (0x4B < 0x80)
+SVS_HD uint32_t bgr_sum_to_float(uint32_t s) { return hw::prmt(s, s, 0x3B2Bu); }
 
 // 8 BGR pixels in six words -> their 8 gray bytes in two words
 SVS_HD void row_gray_words(const uint32_t* w, uint32_t& glo, uint32_t& ghi)
@@ -129,7 +139,11 @@ SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& 
         bgr_row_sums(v, s);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
+#if SVS_BLK_PRMT1
+            c[j] = hw::pku(bgr_sum_to_float(s[2 * j]), bgr_sum_to_float(s[2 * j + 1]));
+#else
             c[j] = hw::pku(hw::byte_perm(s[2 * j], magic_hi, 0x7524u), hw::byte_perm(s[2 * j + 1], magic_hi, 0x7524u));
+#endif
         if (WANT_GRAY) {
             glo = hw::byte_perm(hw::byte_perm(s[0], s[1], 0x0062u), hw::byte_perm(s[2], s[3], 0x0062u), 0x5410u);
             ghi = hw::byte_perm(hw::byte_perm(s[4], s[5], 0x0062u), hw::byte_perm(s[6], s[7], 0x0062u), 0x5410u);
@@ -671,29 +685,56 @@ __device__ __forceinline__ void prefetch_rows_l2(const BlkGeom& G, const Where& 
 }
 
 // cp.async staging: slot (r, j) of thread t is 8 bytes at ((r*P + j) * kBlkThreads + t) * 8 of the
-// dynamic shared memory - thread-private, conflict-free, no barrier needed.
+// dynamic shared memory - thread-private, conflict-free, no barrier needed.  The slot and word
+// offsets are compile-time immediates of the instructions (no address arithmetic per access).
+template <int SLOT_OFF, int SRC_OFF>
+__device__ __forceinline__ void cp_async8(uint32_t slot0, const uint8_t* p)
+{
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 8;" ::"r"(slot0), "l"(p), "n"(SLOT_OFF), "n"(SRC_OFF) : "memory");
+}
+template <int SLOT_OFF>
+__device__ __forceinline__ void lds8(uint32_t slot0, uint32_t& lo, uint32_t& hi)
+{
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2 + %3];" : "=r"(lo), "=r"(hi) : "r"(slot0), "n"(SLOT_OFF) : "memory");
+}
+template <int CH, int R>
+__device__ __forceinline__ void stage_request_row(uint32_t slot0, const uint8_t* p)
+{
+    constexpr int P = CH == 3 ? 3 : 1;
+    cp_async8<(R * P + 0) * kBlkThreads * 8, 0>(slot0, p);
+    if (CH == 3) {
+        cp_async8<(R * P + 1) * kBlkThreads * 8, 8>(slot0, p);
+        cp_async8<(R * P + 2) * kBlkThreads * 8, 16>(slot0, p);
+    }
+}
 template <int CH>
 __device__ __forceinline__ void stage_request(const BlkGeom& G, const Where& w, uint32_t slot0)
 {
-    constexpr int P = CH == 3 ? 3 : 1;
     const uint8_t* p = block_src<CH>(G, w);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int j = 0; j < P; ++j)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot0 + (uint32_t)((r * P + j) * kBlkThreads * 8)), "l"(p + 8 * j) : "memory");
-        p += G.row_stride;
-    }
+    stage_request_row<CH, 0>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 1>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 2>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 3>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 4>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 5>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 6>(slot0, p); p += G.row_stride;
+    stage_request_row<CH, 7>(slot0, p);
     asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int CH, int K>
+__device__ __forceinline__ void stage_fetch_from(uint32_t slot0, uint32_t* rows)
+{
+    constexpr int N = 8 * (CH == 3 ? 3 : 1);
+    if constexpr (K < N) {
+        lds8<K * kBlkThreads * 8>(slot0, rows[2 * K], rows[2 * K + 1]);
+        stage_fetch_from<CH, K + 1>(slot0, rows);
+    }
 }
 template <int CH>
 __device__ __forceinline__ void stage_fetch(uint32_t slot0, uint32_t* rows)
 {
-    constexpr int P = CH == 3 ? 3 : 1;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < 8 * P; ++k)
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rows[2 * k]), "=r"(rows[2 * k + 1]) : "r"(slot0 + (uint32_t)(k * kBlkThreads * 8)) : "memory");
+    stage_fetch_from<CH, 0>(slot0, rows);
 }
 
 // the three payload words that hold the block's 64-bit window, as loaded (big-endian bit order inside bytes)
