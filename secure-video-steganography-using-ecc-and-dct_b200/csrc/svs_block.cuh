@@ -557,11 +557,15 @@ SVS_HD void block_extract(const uint32_t* rows, uint32_t magic_hi, const QuantRe
 // ==========================================================================================
 // kernels
 // ==========================================================================================
+// ONE CTA of 16 warps per SM.  Two CTAs of 8 warps hold the same 16 warps, but the warp scheduler
+// prefers the older CTA: it finished its share at ~60 % of the kernel time and the younger one ran
+// the rest alone (ncu: 3.2 of 4 warp slots per sub-partition occupied on average, 4.0 with one
+// CTA; embed 1.57 -> 1.50, extract 0.82 -> 0.79 ms per 600 frames).
 #ifndef SVS_BLK_THREADS
-#define SVS_BLK_THREADS 256
+#define SVS_BLK_THREADS 512
 #endif
 #ifndef SVS_BLK_MIN_CTAS
-#define SVS_BLK_MIN_CTAS 2
+#define SVS_BLK_MIN_CTAS 1
 #endif
 // How the rows of a group reach the registers:
 //   0  LDG at the top of the group (the warp waits for HBM once per group);
@@ -777,6 +781,25 @@ __device__ __forceinline__ void store_row(uint8_t* dst, uint32_t lo4, uint32_t h
 
 extern __shared__ __align__(16) unsigned char blk_dyn_smem[];
 
+// Work distribution inside a CTA (SVS_BLK_TICKETS).  The groups are dealt to the CTAs in rounds of
+// kBlkWarps consecutive groups (round j -> CTA j % gridDim.x), so that all CTAs sweep the batch
+// together; the warps of a CTA draw TICKETS from a shared-memory counter: ticket t = group
+// t % kBlkWarps of the CTA's round t / kBlkWarps.  With warps in step this is the static strided
+// assignment, but warps that get ahead take more tickets instead of finishing early.
+#ifndef SVS_BLK_TICKETS
+#define SVS_BLK_TICKETS 0
+#endif
+__device__ __forceinline__ long long ticket_group(unsigned t)
+{
+    return ((long long)(t / kBlkWarps) * gridDim.x + blockIdx.x) * kBlkWarps + (t % kBlkWarps);
+}
+__device__ __forceinline__ unsigned draw_ticket(unsigned* counter, int lane)
+{
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1u);
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+
 // SIDE: also the gray reference (first return value of the reference function,
 // config_and_setup.py:111-114,172) and / or the per-frame sum of squared differences gray vs
 // stego (what cv2.PSNR needs, embed_process.py:204-206), from the bytes the thread already holds.
@@ -792,6 +815,11 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
     // warp belong to the same frame and its squared-error sum stays in a register until the frame
     // changes - one atomic per warp and frame instead of one per group (1013 same-address atomics
     // per 1080p frame cost 25 % of the kernel).
+#if SVS_BLK_TICKETS
+    __shared__ unsigned tickets;
+    if (threadIdx.x == 0) tickets = kBlkWarps;     // tickets 0 .. kBlkWarps-1 are the warps' first groups
+    __syncthreads();
+#endif
     const long long n_warps = (long long)gridDim.x * kBlkWarps;
     const long long my_warp = (long long)blockIdx.x * kBlkWarps + warp;
     const long long chunk = (G.total_groups + n_warps - 1) / n_warps;
@@ -846,7 +874,11 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
         payload_window(pw, w0, w1);
 
         // the next group of this warp: its rows (and payload words) are requested now
+#if SVS_BLK_TICKETS
+        const long long gn = SIDE ? g + 1 : ticket_group(draw_ticket(&tickets, lane));
+#else
         const long long gn = g + gstep;
+#endif
         const bool more = gn < g_end;
         Where wn = w;
         if (more) {
@@ -929,12 +961,18 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = NP == 4 ? (G.n >= 63 ? 63 : G.n) : G.n;
     const QuantRegs Q = make_quant_regs(a.q, G.delta32);
+#if SVS_BLK_TICKETS
+    __shared__ unsigned tickets;
+    if (threadIdx.x == 0) tickets = kBlkWarps;
+    __syncthreads();
+#endif
     const long long gstep = (long long)gridDim.x * kBlkWarps;
     long long g = (long long)blockIdx.x * kBlkWarps + warp;
     if (g >= G.total_groups) return;
     constexpr bool kStaged = kBlkStage == 2;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(blk_dyn_smem) + threadIdx.x * 8u;
     (void)slot0;
+    (void)gstep;
 
     Where w = locate(G, g, lane);
     uint32_t rows[CH == 3 ? 48 : 16];
@@ -947,7 +985,11 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(c
         P2 c[32];
         block_input<CH, false>(rows, G.magic_hi, c, nullptr);
 
+#if SVS_BLK_TICKETS
+        const long long gn = ticket_group(draw_ticket(&tickets, lane));
+#else
         const long long gn = g + gstep;
+#endif
         const bool more = gn < G.total_groups;
         Where wn = w;
         if (more) {
