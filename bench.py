@@ -391,7 +391,8 @@ def main():
     if gather_mode == "push":
         try:
             overlap = sharding.CopyEngineGather(F, pitch, dev, n_streams=int(os.environ.get("SVS_PUSH_STREAMS", "4")),
-                                                n_buffers=int(os.environ.get("SVS_PUSH_BUFFERS", "2")))
+                                                n_buffers=int(os.environ.get("SVS_PUSH_BUFFERS", "2")),
+                                                use_multicast=os.environ.get("SVS_PUSH_MULTICAST", "1") != "0")
             bits, gathered = overlap.local, overlap.gathered
         except Exception as exc:
             sys.stderr.write("rank %d: symmetric memory unavailable (%r); falling back to NCCL all-gather\n" % (rank, exc))
@@ -575,7 +576,9 @@ def main():
                                "frac": lane_ops / (embed_ms / 1000.0) / fp32_peak,
                                "lane_ops_per_block": fp32_lane_ops_per_block(NUM_AC)},
         "roofline_operand_delivery": None if not prof.get("embed_rf_cycles_per_32_blocks") else {
-            "bound": "register-file operand delivery (2 banks x one 32-bit read per lane and clock; secondary)",
+            "bound": "register-file operand delivery (2 banks x one 32-bit read per lane and clock; secondary). "
+                     "frac = modelled / measured cycles: ~1 means the kernel runs at the modelled operand-delivery rate "
+                     "(the model is good to a few per cent, so slightly above 1 is possible)",
             "model_cycles_per_32_blocks": prof["embed_rf_cycles_per_32_blocks"],
             "measured_cycles_per_32_blocks": embed_ms / 1000.0 * sm_mhz * 1e6 / (F * wl.blocks / 32.0 / (148 * 4)),
             "frac": prof["embed_rf_cycles_per_32_blocks"] / (embed_ms / 1000.0 * sm_mhz * 1e6 / (F * wl.blocks / 32.0 / (148 * 4))),

@@ -174,6 +174,14 @@ int64_t svs_kernel_launch_count(void);
  * previous value.  Process-wide. */
 int svs_set_reserved_sms(int n);
 
+/* Stream-ordered device-to-device copy on the copy engines (cudaMemcpyAsync) between raw device
+ * addresses.  Exists for the multi-GPU exchange of the extracted bit rows (sharding.py): `d_dst`
+ * may be a peer mapping or an NVSwitch MULTICAST address of the gathered buffer - the copy engines
+ * can write to it, and the switch then replicates the rows into every rank's buffer (one outbound
+ * copy instead of one per peer; profiles/microbench/ce_multicast.py).  No counterpart in the
+ * reference (single process). */
+int svs_memcpy_d2d_async(void* d_dst, const void* d_src, int64_t bytes, void* stream);
+
 /* Diagnostic: selects the kernel family, process-wide.  0 = automatic (default: the packed
  * one-block-per-thread kernels of svs_block.cuh whenever they apply, the scalar kernels
  * otherwise), 1 = scalar kernels only, 5 = packed block kernels.  A library built with

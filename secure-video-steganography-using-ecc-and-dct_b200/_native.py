@@ -83,6 +83,7 @@ _SIGNATURES = {
     "svs_bits_row_bytes": (_c.c_int64, [_c.c_int, _c.c_int, _c.c_int]),
     "svs_kernel_launch_count": (_c.c_int64, []),
     "svs_debug_kernel_family": (_c.c_int, [_c.c_int]),
+    "svs_memcpy_d2d_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p]),
     "svs_set_reserved_sms": (_c.c_int, [_c.c_int]),
     "svs_extract_frames": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int64,
                                       _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p]),

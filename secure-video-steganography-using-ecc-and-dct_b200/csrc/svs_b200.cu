@@ -714,6 +714,16 @@ int svs_debug_kernel_family(int family_id)
     return g_family.exchange(family_id);
 }
 
+int svs_memcpy_d2d_async(void* d_dst, const void* d_src, int64_t bytes, void* stream)
+{
+    g_err[0] = 0;
+    if (bytes < 0 || (bytes > 0 && (d_dst == nullptr || d_src == nullptr))) return fail(SVS_ERR_POINTER, "svs_memcpy_d2d_async: bad arguments");
+    if (bytes == 0) return SVS_OK;
+    cudaError_t e = cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "svs_memcpy_d2d_async");
+    return SVS_OK;
+}
+
 int64_t svs_capacity_bits(int height, int width, int num_ac)
 {
     if (height <= 0 || width <= 0) return 0;

@@ -54,15 +54,17 @@ def _worker(rank, world, port, outdir):
                 got = fg.run(res.stego, DELTA, N_AC)[:, :(cap + 7) // 8]
                 torch.cuda.synchronize()
                 assert torch.equal(got, plain), "fused gather (%s) differs" % fg.mode
-        # ... and the copy-engine variant (DMA pushes on side streams, overlappable with the next batch)
-        cg = sharding.CopyEngineGather(f1 - f0, svs_b200.bits_row_bytes(H, W, N_AC), mine.device, n_streams=2)
-        for _ in range(2):
-            cg.gathered.zero_()
-            cg.hdl.barrier(channel=2)
-            cg.run(res.stego, DELTA, N_AC)
-            got = cg.wait()[:, :(cap + 7) // 8]
-            torch.cuda.synchronize()
-            assert torch.equal(got, plain), "copy-engine gather differs"
+        # ... and the copy-engine variants (DMA pushes on side streams, overlappable with the next batch):
+        # one copy per peer, and ONE copy to the NVSwitch multicast address of this rank's rows
+        for mc in (False, "force"):
+            cg = sharding.CopyEngineGather(f1 - f0, svs_b200.bits_row_bytes(H, W, N_AC), mine.device, n_streams=2, use_multicast=mc)
+            for _ in range(3):                               # three rounds over two buffers: covers buffer reuse
+                cg.gathered.zero_()
+                cg.hdl.barrier(channel=2)
+                cg.run(res.stego, DELTA, N_AC)
+                got = cg.wait()[:, :(cap + 7) // 8]
+                torch.cuda.synchronize()
+                assert torch.equal(got, plain), "copy-engine gather differs (%s)" % cg.mode
         np.save(os.path.join(outdir, "bits%d.npy" % rank), full.cpu().numpy())
         np.save(os.path.join(outdir, "stego%d.npy" % rank), res.stego.cpu().numpy())
     finally:
