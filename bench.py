@@ -392,7 +392,7 @@ def main():
         try:
             overlap = sharding.CopyEngineGather(F, pitch, dev, n_streams=int(os.environ.get("SVS_PUSH_STREAMS", "4")),
                                                 n_buffers=int(os.environ.get("SVS_PUSH_BUFFERS", "2")),
-                                                use_multicast=os.environ.get("SVS_PUSH_MULTICAST", "1") != "0")
+                                                use_multicast=os.environ.get("SVS_PUSH_MULTICAST", "0") == "1")
             bits, gathered = overlap.local, overlap.gathered
         except Exception as exc:
             sys.stderr.write("rank %d: symmetric memory unavailable (%r); falling back to NCCL all-gather\n" % (rank, exc))

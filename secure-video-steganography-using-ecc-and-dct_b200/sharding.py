@@ -219,7 +219,7 @@ class CopyEngineGather:
     are the buffers of the latest `run()`.
     """
 
-    def __init__(self, n_local, pitch, device, group=None, n_streams=4, n_buffers=2, use_multicast=True):
+    def __init__(self, n_local, pitch, device, group=None, n_streams=4, n_buffers=2, use_multicast=False):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -233,17 +233,18 @@ class CopyEngineGather:
         for _ in range(max(1, int(n_buffers))):
             g = symm.empty(shape, dtype=torch.uint8, device=device)
             hdl = symm.rendezvous(g, self.group)
-            # (with two ranks a single per-peer copy is faster than going through the switch's multicast
-            #  path: 0.66 vs 1.43 ms for 460 MB; use_multicast="force" is for the 2-GPU test)
+            # (use_multicast="force": also with two ranks, where one peer copy is much faster - 0.66 vs
+            #  1.43 ms for 460 MB; that is what the 2-GPU test uses)
             want_mc = use_multicast == "force" or (bool(use_multicast) and self.world > 2)
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if want_mc else 0
             b = {"gathered": g, "hdl": hdl, "done": None, "mc": 0}
             if mc:
-                # NVSwitch multicast: the extract kernel writes into a PRIVATE staging buffer and ONE
-                # copy-engine copy per stream sends it to the multicast address of this rank's rows -
-                # the switch replicates them into every rank's buffer, this rank's included (so source
-                # and destination never overlap).  1/(world-1) of the outbound traffic and HBM reads of
-                # the per-peer pushes; measured on 8 x B200 in DESIGN.md section 5.
+                # NVSwitch multicast (OFF by default): the extract kernel writes into a PRIVATE staging
+                # buffer and ONE copy-engine copy per stream sends it to the multicast address of this
+                # rank's rows - the switch replicates them into every rank's buffer, this rank's included
+                # (so source and destination never overlap).  1/(world-1) of the outbound traffic and HBM
+                # reads of the per-peer pushes, but MEASURED SLOWER on 8 x B200: 1,717,456 frames/s against
+                # 1,944,604 with one copy per peer (the exchange takes 8.4 instead of 7.4 ms per step).
                 b["mc"] = mc + r0 * self.pitch
                 b["local"] = torch.empty((self.n_local, self.pitch), dtype=torch.uint8, device=device)
                 b["peers"] = []
