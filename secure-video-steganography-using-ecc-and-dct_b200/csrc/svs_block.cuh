@@ -184,14 +184,15 @@ SVS_HD void columns_fwd_pruned(const PackedOps& po, P2 (&c)[32])
 
 // rows 2i and 2i+1 of the column-pair layout (ra, rb: 4 pairs each) through scalar stage 1 ->
 // the eight stage-1 values of both rows, packed (lo = row 2i, hi = row 2i+1)
-template <bool INVERSE>
+// FAR: pair j of a row holds columns (j, j+4) instead of (2j, 2j+1) (see SVS_BLK_PAIRING)
+template <bool INVERSE, bool FAR = false>
 SVS_HD Stage1<P2> regroup_rows(const ScalarOps& so, const P2* ra, const P2* rb)
 {
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        hw::unpkf(ra[j], a[2 * j], a[2 * j + 1]);
-        hw::unpkf(rb[j], b[2 * j], b[2 * j + 1]);
+        hw::unpkf(ra[j], a[FAR ? j : 2 * j], a[FAR ? j + 4 : 2 * j + 1]);
+        hw::unpkf(rb[j], b[FAR ? j : 2 * j], b[FAR ? j + 4 : 2 * j + 1]);
     }
     const Stage1<float> ha = INVERSE ? svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7])
                                      : svs::dct8_fwd_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
@@ -208,6 +209,27 @@ SVS_HD void rows_fwd_pair(const PackedOps& po, const ScalarOps& so, const P2* c8
 {
     svs::dct8_fwd_tail(po, regroup_rows<false>(so, c8, c8 + 4), X);
 }
+// ... any two rows (4 column pairs each): X[v] = (coefficient (row a, v), coefficient (row b, v))
+SVS_HD void rows_fwd_two(const PackedOps& po, const ScalarOps& so, const P2* ra, const P2* rb, P2 (&X)[8])
+{
+    svs::dct8_fwd_tail(po, regroup_rows<false>(so, ra, rb), X);
+}
+
+// SVS_BLK_PAIRING = 1 (embed only): which rows / columns share a register pair is chosen so that
+// the SCALAR first stage of the two inverse passes never adds two registers of the same bank.
+// That stage combines inputs (1,7), (2,6), (3,5): with neighbours paired - (2i, 2i+1) - both sit in
+// the same half of their pairs, i.e. in registers of equal parity, and the add takes two
+// operand-delivery cycles instead of one (96 such adds per block).  With rows paired (i, i+4) for
+// the forward row pass / quantiser and columns paired (j, j+4) on the way out of the inverse
+// column pass, every one of them reads one even and one odd register.
+// MEASURED: slower (embed 1.544 vs 1.507 ms per 600 frames at 63 AC, 1.433 vs 1.370 at 10 AC) - two of
+// the three tie-prone coefficients move into the high halves and the register allocator needs more
+// moves; the bank conflicts it removes were not what limits the kernel.  OFF; both pairings are
+// compiled into the host tests (tests/test_block_host.py).
+#ifndef SVS_BLK_PAIRING
+#define SVS_BLK_PAIRING 0
+#endif
+constexpr bool kFarPairs = SVS_BLK_PAIRING != 0;
 
 // axis 0, inverse, columns 2j and 2j+1: reads the row-pair layout q, writes column pairs c[r*4+j]
 SVS_HD void columns_inv_pair(const PackedOps& po, const ScalarOps& so, const P2 (&q)[32], int j, P2 (&c)[32])
@@ -229,10 +251,33 @@ SVS_HD void columns_inv_pair(const PackedOps& po, const ScalarOps& so, const P2 
     for (int r = 0; r < 8; ++r) c[4 * r + j] = x[r];
 }
 
+// the same for the (i, i+4) row pairs / (j, j+4) column pairs of SVS_BLK_PAIRING: q[8i + col] =
+// (coefficient (i, col), coefficient (i+4, col)); transform j handles columns j and j+4 and writes
+// c[4r + j] = (x[r][j], x[r][j+4])
+SVS_HD void columns_inv_pair_far(const PackedOps& po, const ScalarOps& so, const P2 (&q)[32], int j, P2 (&c)[32])
+{
+    float a[8], b[8];                         // coefficient columns j and j+4, u = 0..7
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hw::unpkf(q[8 * i + j], a[i], a[i + 4]);
+        hw::unpkf(q[8 * i + j + 4], b[i], b[i + 4]);
+    }
+    const Stage1<float> ha = svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    const Stage1<float> hb = svs::dct8_inv_head(so, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    Stage1<P2> h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h.v[k] = hw::pk(ha.v[k], hb.v[k]);
+    P2 x[8];
+    svs::dct8_inv_tail(po, h, x);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) c[4 * r + j] = x[r];
+}
+
 // axis 1, inverse, rows 2i and 2i+1: out[col] = (pixel (2i, col), pixel (2i+1, col))
+template <bool FAR = false>
 SVS_HD void rows_inv_pair(const PackedOps& po, const ScalarOps& so, const P2* c8, P2 (&out)[8])
 {
-    svs::dct8_inv_tail(po, regroup_rows<true>(so, c8, c8 + 4), out);
+    svs::dct8_inv_tail(po, regroup_rows<true, FAR>(so, c8, c8 + 4), out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -277,14 +322,15 @@ SVS_HD uint32_t window_bit(uint32_t w0, uint32_t w1, int idx) { return ((idx < 3
 // even, float32 product) and patched into `res`.  Scalars only (an array indexed by the lane
 // would live in local memory): a call costs 8 loads of `orig` and touches `res` only where a
 // coefficient is actually flagged.
-SVS_RARE void fix_pair_embed(const P2* orig, P2* res, int i, int n, float d, float r, float r2, float ke, uint32_t emask,
-                    uint32_t w0, uint32_t w1)
+// Payload bit numbers of the two halves of pair v: base + v and base + v + hi_off.
+SVS_RARE void fix_pair_embed(const P2* orig, P2* res, int base, int hi_off, int n, float d, float r, float r2, float ke,
+                    uint32_t emask, uint32_t w0, uint32_t w1)
 {
 #pragma unroll 1
     for (int v = 0; v < 8; ++v) {
         float ca, cb;
         hw::unpkf(orig[v], ca, cb);
-        const int ia = 16 * i + v - 1, ib = ia + 8;
+        const int ia = base + v, ib = ia + hi_off;
         const bool fa = ia >= 0 && ia < n && (hw::f2u(hw::ffma(ca, r2, ke)) & emask) < kZone;
         const bool fb = ib < n && (hw::f2u(hw::ffma(cb, r2, ke)) & emask) < kZone;
         if (!(fa || fb)) continue;
@@ -327,31 +373,34 @@ SVS_RARE uint32_t fix_pair_extract(const P2* in, uint32_t rows, int i, int n, fl
 // 8u + v - 1 goes to coefficient (u, v): row-major flat index 1..n (config_and_setup.py:138-141).
 // p0/p1 are the window words pre-rotated so that bit idx sits `idx` places below position
 // erot: bringing it there is a rotate by the compile-time constant idx.
-template <bool NFULL>
+template <bool NFULL, bool FAR>
 SVS_HD void quant_embed_pair(int i, P2 (&X)[8], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t p0, uint32_t p1)
 {
+    // halves of pair v: coefficient rows (2i, 2i+1), or (i, i+4) with FAR
+    const int base = (FAR ? 8 : 16) * i - 1, hi_off = FAR ? 32 : 8;
     uint32_t worst = 0xffffffffu;
     P2 nx[8];
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
-        const int il = 16 * i + v - 1, ih = il + 8;             // payload bit numbers of the two halves
-        const bool tie = tie_prone(16 * i + v);                 // only ever the low half
+        const int il = base + v, ih = il + hi_off;              // payload bit numbers of the two halves
+        const bool tl = tie_prone(il + 1), th = tie_prone(ih + 1);
         const bool al = il >= 0 && (NFULL || il < n), ah = NFULL || ih < n;
         const P2 y = hw::fma2(X[v], Q.r2, Q.ke);
         uint32_t ya, yb;
         hw::unpk(y, ya, yb);
-        if (al && !tie) worst = hw::umin(worst, ya & Q.emask);
-        if (ah) worst = hw::umin(worst, yb & Q.emask);
+        if (al && !tl) worst = hw::umin(worst, ya & Q.emask);
+        if (ah && !th) worst = hw::umin(worst, yb & Q.emask);
         const int jl = il < 0 ? 0 : il;
         const uint32_t ta = hw::funnel_l(jl < 32 ? p0 : p1, jl < 32 ? p0 : p1, jl & 31) & Q.ebit;
         const uint32_t tb = hw::funnel_l(ih < 32 ? p0 : p1, ih < 32 ? p0 : p1, ih & 31) & Q.ebit;
         // M + floor() + bit/2, then (2e + bit) * delta in one rounding
         const P2 z = hw::fma2(hw::pku((ya & ~Q.emask) | ta, (yb & ~Q.emask) | tb), Q.d2, Q.k0);
-        if (NFULL && !tie && il >= 0) {
+        if (NFULL && !tl && !th && il >= 0) {
             nx[v] = z;
         } else {
             float lo = hw::lo_of(z), hi = hw::hi_of(z);
-            if (tie) lo = exact_embed(hw::lo_of(X[v]), window_bit(w0, w1, jl), Q);
+            if (tl) lo = exact_embed(hw::lo_of(X[v]), window_bit(w0, w1, jl), Q);
+            if (th) hi = exact_embed(hw::hi_of(X[v]), window_bit(w0, w1, ih), Q);
             if (!al) lo = hw::lo_of(X[v]);
             if (!ah) hi = hw::hi_of(X[v]);
             nx[v] = hw::pk(lo, hi);
@@ -362,7 +411,7 @@ SVS_HD void quant_embed_pair(int i, P2 (&X)[8], const QuantRegs& Q, int n, uint3
         P2 orig[8], res[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) { orig[v] = X[v]; res[v] = nx[v]; }
-        fix_pair_embed(orig, res, i, NFULL ? 63 : n, Q.d, Q.r, Q.r2s, Q.kes, Q.emask, w0, w1);
+        fix_pair_embed(orig, res, base, hi_off, NFULL ? 63 : n, Q.d, Q.r, Q.r2s, Q.kes, Q.emask, w0, w1);
 #pragma unroll
         for (int v = 0; v < 8; ++v) nx[v] = res[v];
     }
@@ -429,12 +478,13 @@ SVS_HD void block_input(const uint32_t* rows, uint32_t magic_hi, P2 (&c)[32], ui
 
 // Forward 2-D transform of the block (column pairs c, destroyed) and embedding of its n payload
 // bits: q = the quantised coefficients as row pairs.  Every block coming here takes all n bits.
-// SVS_BLK_QPIPE: the axis-1 transform of row pair i+1 is issued before row pair i is quantised,
-// so that FP32 work and the quantiser's integer work sit in the same basic block.
+// SVS_BLK_QPIPE (extract only, experiment, OFF): the axis-1 transform of row pair i+1 is issued before
+// row pair i is quantised, so that FP32 work and the quantiser's integer work sit in the same basic
+// block.  MEASURED: no gain (DESIGN.md / profiles/README.md).
 #ifndef SVS_BLK_QPIPE
 #define SVS_BLK_QPIPE 0
 #endif
-template <bool NFULL>
+template <bool NFULL, bool FAR = kFarPairs>
 SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, P2 (&q)[32])
 {
     const PackedOps po;
@@ -442,41 +492,34 @@ SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
     columns_fwd(po, c);
     const int pre = (Q.erot - 31) & 31;
     const uint32_t p0 = hw::funnel_l(w0, w0, pre), p1 = hw::funnel_l(w1, w1, pre);
-#if SVS_BLK_QPIPE
-    P2 X[2][8];
-    rows_fwd_pair(po, so, c, X[0]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (i < 3) rows_fwd_pair(po, so, c + 8 * (i + 1), X[(i + 1) & 1]);
-        if (NFULL || 16 * i - 1 < n) quant_embed_pair<NFULL>(i, X[i & 1], Q, n, w0, w1, p0, p1);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) q[8 * i + v] = X[i & 1][v];
-    }
-#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         P2 X[8];
-        rows_fwd_pair(po, so, c + 8 * i, X);
-        if (NFULL || 16 * i - 1 < n) quant_embed_pair<NFULL>(i, X, Q, n, w0, w1, p0, p1);
+        if (FAR) rows_fwd_two(po, so, c + 4 * i, c + 4 * (i + 4), X);       // rows i and i+4
+        else rows_fwd_pair(po, so, c + 8 * i, X);                          // rows 2i and 2i+1
+        if (NFULL || (FAR ? 8 : 16) * i - 1 < n) quant_embed_pair<NFULL, FAR>(i, X, Q, n, w0, w1, p0, p1);
 #pragma unroll
         for (int v = 0; v < 8; ++v) q[8 * i + v] = X[v];
     }
-#endif
 }
 
 // Inverse 2-D transform of the row pairs q (destroyed) and conversion to bytes:
 // stego = 16 words, row r at [2r], [2r+1].
+template <bool FAR = kFarPairs>
 SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
 {
     const PackedOps po;
     const ScalarOps so;
     P2 c[32];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) columns_inv_pair(po, so, q, j, c);
+    for (int j = 0; j < 4; ++j) {
+        if (FAR) columns_inv_pair_far(po, so, q, j, c);
+        else columns_inv_pair(po, so, q, j, c);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         P2 o[8];
-        rows_inv_pair(po, so, c + 8 * i, o);
+        rows_inv_pair<FAR>(po, so, c + 8 * i, o);
         uint32_t ba[8], bb[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -491,21 +534,21 @@ SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
     }
 }
 
-template <bool NFULL>
+template <bool NFULL, bool FAR = kFarPairs>
 SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t* stego)
 {
     P2 q[32];
-    block_forward_quant<NFULL>(c, Q, n, w0, w1, q);
-    block_inverse(q, stego);
+    block_forward_quant<NFULL, FAR>(c, Q, n, w0, w1, q);
+    block_inverse<FAR>(q, stego);
 }
 
-template <int CH, bool NFULL, bool WANT_GRAY>
+template <int CH, bool NFULL, bool WANT_GRAY, bool FAR = kFarPairs>
 SVS_HD void block_embed(const uint32_t* rows, uint32_t magic_hi, const QuantRegs& Q, int n, uint32_t w0, uint32_t w1,
                         uint32_t* stego, uint32_t* gray)
 {
     P2 c[32];
     block_input<CH, WANT_GRAY>(rows, magic_hi, c, gray);
-    block_embed_pairs<NFULL>(c, Q, n, w0, w1, stego);
+    block_embed_pairs<NFULL, FAR>(c, Q, n, w0, w1, stego);
 }
 
 // NP = number of coefficient row pairs that hold any of the n coefficients: ceil((n + 1) / 16).
