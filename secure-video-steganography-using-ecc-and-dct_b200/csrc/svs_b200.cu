@@ -561,6 +561,8 @@ blk::BlkGeom make_blk_geometry(const Geometry& g, long long n_frames)
     b.frames = g.frames;
     b.frame_stride = g.frame_stride;
     b.row_stride = g.row_stride;
+    b.frame_stride32 = (uint32_t)g.frame_stride;
+    b.row_stride32 = (uint32_t)g.row_stride;
     b.bw = g.bw;
     b.bpf = g.bpf;
     b.n = g.n;
@@ -571,6 +573,15 @@ blk::BlkGeom make_blk_geometry(const Geometry& g, long long n_frames)
     b.magic_hi = 0x4B000000u;
     b.delta32 = g.delta32;
     return b;
+}
+
+// The block kernels address inside a frame with 32-bit offsets: the frame extent and (for more
+// than one frame) the distance between frames have to fit.  Anything else - no real video comes
+// close - goes to the scalar kernels.
+bool blk_addressable(long long n_frames, int H, long long frame_stride, long long row_stride)
+{
+    const long long lim = 0xffffffffLL;
+    return (long long)H * row_stride <= lim && (n_frames <= 1 || frame_stride <= lim);
 }
 
 // persistent grid: kBlkMinCtas CTAs on every usable SM (or fewer when there is not enough work)
@@ -763,7 +774,8 @@ static int extract_impl(const uint8_t* d_frames, int channels, int64_t n_frames,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const svs::FastQuant fq = make_fast_quant(delta);
     const int fam = family();
-    if (fam != 1 && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 31) / 32) < 0x7fffffffLL) {
+    if (fam != 1 && al && words && delta > 0 && fq.extract_ok && n_frames * ((a.g.bpf + 31) / 32) < 0x7fffffffLL &&
+        blk_addressable(n_frames, height, frame_stride, row_stride)) {
         cudaError_t fe = cudaSuccess;
         if (fam == 0 || fam == 5) {
             blk::BlkExtractArgs xa;
@@ -925,7 +937,8 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
         if (full > n_frames) full = n_frames;
         bool done = false;
         const bool nfull = a.g.n == SVS_MAX_AC;
-        if (full > 0 && (fam == 0 || fam == 5)) {
+        if (full > 0 && (fam == 0 || fam == 5) && blk_addressable(full, height, frame_stride, row_stride) &&
+            blk_addressable(full, height, stego_frame_stride, stego_row_stride) && a.payload_last_word < 0xfffffff0LL) {
             // block kernels: gray / SSE come from the bytes the thread already holds (SIDE instantiation)
             blk::BlkEmbedArgs ba;
             ba.g = make_blk_geometry(a.g, full);
@@ -937,6 +950,8 @@ int svs_embed_frames(const uint8_t* d_frames, int channels, int64_t n_frames,
             ba.stego = d_stego_out;
             ba.stego_frame_stride = stego_frame_stride;
             ba.stego_row_stride = stego_row_stride;
+            ba.stego_frame_stride32 = (uint32_t)stego_frame_stride;
+            ba.stego_row_stride32 = (uint32_t)stego_row_stride;
             ba.bits_embedded = d_bits_embedded_out;
             ba.gray = d_gray_out;
             ba.sse = d_sse_out;

@@ -520,16 +520,11 @@ SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
     for (int i = 0; i < 4; ++i) {
         P2 o[8];
         rows_inv_pair<FAR>(po, so, c + 8 * i, o);
-        uint32_t ba[8], bb[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            ba[k] = hw::to_u8(hw::lo_of(o[k]));                 // clip then truncate (config_and_setup.py:171)
-            bb[k] = hw::to_u8(hw::hi_of(o[k]));
-        }
+        // clip then truncate (config_and_setup.py:171); low halves = row 2i, high halves = row 2i+1
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            stego[4 * i + h] = hw::byte_perm(hw::byte_perm(ba[4 * h], ba[4 * h + 1], 0x0040u), hw::byte_perm(ba[4 * h + 2], ba[4 * h + 3], 0x0040u), 0x5410u);
-            stego[4 * i + 2 + h] = hw::byte_perm(hw::byte_perm(bb[4 * h], bb[4 * h + 1], 0x0040u), hw::byte_perm(bb[4 * h + 2], bb[4 * h + 3], 0x0040u), 0x5410u);
+            stego[4 * i + h] = hw::pack4_u8(hw::lo_of(o[4 * h]), hw::lo_of(o[4 * h + 1]), hw::lo_of(o[4 * h + 2]), hw::lo_of(o[4 * h + 3]));
+            stego[4 * i + 2 + h] = hw::pack4_u8(hw::hi_of(o[4 * h]), hw::hi_of(o[4 * h + 1]), hw::hi_of(o[4 * h + 2]), hw::hi_of(o[4 * h + 3]));
         }
     }
 }
@@ -644,6 +639,7 @@ __host__ __device__ constexpr int blk_embed_smem_bytes() { return blk_smem_bytes
 struct BlkGeom {
     const uint8_t* frames;
     long long frame_stride, row_stride;
+    uint32_t frame_stride32, row_stride32;        // the same, when SVS_BLK_ADDR32 (the launcher checks that they fit)
     int bw, bpf, n;
     int gpf;                                      // groups per frame = ceil(bpf / 32)
     long long total_groups;                       // n_frames * gpf, < 2^31
@@ -659,6 +655,7 @@ struct BlkEmbedArgs {
     long long payload_bit_offset, payload_last_word, cap;
     uint8_t* stego;
     long long stego_frame_stride, stego_row_stride;
+    uint32_t stego_frame_stride32, stego_row_stride32;
     int64_t* bits_embedded;
     uint8_t* gray;                                // nullable; contiguous H x W frames   (SIDE kernels only)
     unsigned long long* sse;                      // nullable; per-frame sum of squares  (SIDE kernels only)
@@ -696,10 +693,36 @@ __device__ __forceinline__ Where locate(const BlkGeom& G, long long g, int lane)
     return w;
 }
 
+// SVS_BLK_ADDR32: a frame spans less than 4 GB, so the offset of a block inside its frame and the
+// offsets of its 8 rows are 32-bit values (the row offsets r * stride are warp-uniform and loop-
+// invariant: uniform registers) - one 64-bit add per row instead of two, no 64-bit multiplies.
+#ifndef SVS_BLK_ADDR32
+#define SVS_BLK_ADDR32 1
+#endif
+template <typename T>
+__device__ __forceinline__ T* frame_ptr(T* base, int f, uint32_t frame_stride, uint32_t in_frame)
+{
+    return base + ((unsigned long long)(uint32_t)f * frame_stride + in_frame);
+}
 template <int CH>
 __device__ __forceinline__ const uint8_t* block_src(const BlkGeom& G, const Where& w)
 {
+#if SVS_BLK_ADDR32
+    return frame_ptr(G.frames, w.f, G.frame_stride32, (uint32_t)(w.by * 8) * G.row_stride32 + (uint32_t)(w.bx * (8 * CH)));
+#else
     return G.frames + w.f * G.frame_stride + (long long)(w.by * 8) * G.row_stride + w.bx * (8 * CH);
+#endif
+}
+template <typename T>
+__device__ __forceinline__ T* row_ptr(T* p, int r, long long stride, uint32_t stride32)
+{
+#if SVS_BLK_ADDR32
+    (void)stride;
+    return p + (uint32_t)r * stride32;
+#else
+    (void)stride32;
+    return p + r * stride;
+#endif
 }
 
 template <int CH>
@@ -758,14 +781,14 @@ template <int CH>
 __device__ __forceinline__ void stage_request(const BlkGeom& G, const Where& w, uint32_t slot0)
 {
     const uint8_t* p = block_src<CH>(G, w);
-    stage_request_row<CH, 0>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 1>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 2>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 3>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 4>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 5>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 6>(slot0, p); p += G.row_stride;
-    stage_request_row<CH, 7>(slot0, p);
+    stage_request_row<CH, 0>(slot0, p);
+    stage_request_row<CH, 1>(slot0, row_ptr(p, 1, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 2>(slot0, row_ptr(p, 2, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 3>(slot0, row_ptr(p, 3, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 4>(slot0, row_ptr(p, 4, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 5>(slot0, row_ptr(p, 5, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 6>(slot0, row_ptr(p, 6, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 7>(slot0, row_ptr(p, 7, G.row_stride, G.row_stride32));
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 template <int CH, int K>
@@ -791,11 +814,21 @@ struct PayWords {
 __device__ __forceinline__ PayWords payload_request(const uint32_t* __restrict__ words, long long last_word, long long pos)
 {
     PayWords p;
+#if SVS_BLK_ADDR32
+    // word indices fit 32 bits (launcher), and the first word of a block the payload fills exists
+    const uint32_t wi = (uint32_t)((unsigned long long)pos >> 5), left = (uint32_t)last_word - wi;
+    const uint32_t* q = words + wi;
+    p.s = (uint32_t)pos & 31u;
+    p.a = __ldg(q);
+    p.b = left >= 1u ? __ldg(q + 1) : 0u;
+    p.c = left >= 2u ? __ldg(q + 2) : 0u;
+#else
     const long long wi = pos >> 5;
     p.s = (uint32_t)(pos & 31);
     p.a = wi <= last_word ? __ldg(words + wi) : 0u;
     p.b = wi + 1 <= last_word ? __ldg(words + wi + 1) : 0u;
     p.c = wi + 2 <= last_word ? __ldg(words + wi + 2) : 0u;
+#endif
     return p;
 }
 __device__ __forceinline__ void payload_window(const PayWords& p, uint32_t& w0, uint32_t& w1)
@@ -829,6 +862,9 @@ extern __shared__ __align__(16) unsigned char blk_dyn_smem[];
 // together; the warps of a CTA draw TICKETS from a shared-memory counter: ticket t = group
 // t % kBlkWarps of the CTA's round t / kBlkWarps.  With warps in step this is the static strided
 // assignment, but warps that get ahead take more tickets instead of finishing early.
+#ifndef SVS_BLK_PIN_D2
+#define SVS_BLK_PIN_D2 1
+#endif
 #ifndef SVS_BLK_TICKETS
 #define SVS_BLK_TICKETS 0
 #endif
@@ -852,7 +888,18 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
     const BlkGeom& G = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = NFULL ? 63 : G.n;
-    const QuantRegs Q = make_quant_regs(a.q, G.delta32);
+    QuantRegs Q = make_quant_regs(a.q, G.delta32);
+#if SVS_BLK_PIN_D2
+    {   // FFMA2 takes one uniform-register operand: with k0 there, 2*delta has to sit in a register.
+        // Left alone ptxas re-creates it (MOV R, UR) in front of every one of the 32 FFMA2 of the
+        // quantiser; an opaque move makes it a value that can only be kept.
+        __shared__ uint32_t pin;
+        uint32_t d2;
+        asm volatile("st.volatile.shared.u32 [%1], %2;\n\tld.volatile.shared.u32 %0, [%1];"
+                     : "=r"(d2) : "r"((uint32_t)__cvta_generic_to_shared(&pin)), "r"(hw::f2u(a.q.d2)) : "memory");
+        Q.d2 = hw::pku(d2, d2);
+    }
+#endif
     // Plain kernels: warp i takes groups i, i + #warps, ... (all warps sweep the batch together).
     // SIDE kernels: warp i takes the CONTIGUOUS range [i K, (i+1) K) so that consecutive groups of a
     // warp belong to the same frame and its squared-error sum stays in a register until the frame
@@ -903,9 +950,13 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
             block_input<CH, SIDE>(rows, G.magic_hi, c, gray);
             if (SIDE) {
                 if (a.gray != nullptr && w.ok) {
+#if SVS_BLK_ADDR32
+                    uint8_t* gd = frame_ptr(a.gray, w.f, (uint32_t)a.gray_frame_stride, (uint32_t)(w.by * 8) * (uint32_t)a.W + (uint32_t)(w.bx * 8));
+#else
                     uint8_t* gd = a.gray + w.f * a.gray_frame_stride + (long long)(w.by * 8) * a.W + w.bx * 8;
+#endif
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) stg64(gd + (long long)r * a.W, gray[2 * r], gray[2 * r + 1]);
+                    for (int r = 0; r < 8; ++r) stg64(row_ptr(gd, r, a.W, (uint32_t)a.W), gray[2 * r], gray[2 * r + 1]);
                 }
                 if (a.sse != nullptr) {
 #pragma unroll
@@ -937,12 +988,15 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
         if (more && kStaged) pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
         block_inverse(q, stego);
         if (w.ok) {
+#if SVS_BLK_ADDR32
+            uint8_t* dst = frame_ptr(a.stego, w.f, a.stego_frame_stride32,
+                                     (uint32_t)(w.by * 8) * a.stego_row_stride32 + (uint32_t)(w.bx * (8 * OUT_CH)));
+#else
             uint8_t* dst = a.stego + w.f * a.stego_frame_stride + (long long)(w.by * 8) * a.stego_row_stride + w.bx * (8 * OUT_CH);
+#endif
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                store_row<OUT_CH>(dst, stego[2 * r], stego[2 * r + 1]);
-                dst += a.stego_row_stride;
-            }
+            for (int r = 0; r < 8; ++r)
+                store_row<OUT_CH>(row_ptr(dst, r, a.stego_row_stride, a.stego_row_stride32), stego[2 * r], stego[2 * r + 1]);
         }
         if (SIDE) {
             if (a.sse != nullptr) {
