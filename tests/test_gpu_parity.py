@@ -163,6 +163,46 @@ def test_narrow_frames_and_unpadded_payloads(kernel_family):
             svs_b200.embed_frames(_dev(frames), _dev(packed[:-1]), total, delta, n)
 
 
+def test_outputs_stay_inside_their_buffers(kernel_family):
+    """Guard bands: stego and bit rows are written into the middle of 0xA5-filled buffers; ragged
+    shapes (a single 8x8 block, blocks per frame not a multiple of 32, W/8 odd), both stego
+    layouts, few and all coefficients, a payload that ends inside the last frame.  Nothing
+    outside the announced rows may change, and the inside must match the oracle."""
+    torch = _torch()
+    guard = 4096
+    for shape in ((1, 8, 8, 3), (3, 40, 72, 3), (2, 136, 264), (5, 24, 1048, 3)):
+        frames = synth_frames("guard%s" % (shape,), shape)
+        nf, h, w = shape[:3]
+        for n, cut in ((63, 0), (10, 0), (63, 77)):
+            delta = 20
+            cap = svs_b200.capacity_bits(h, w, n)
+            total = nf * cap - cut
+            if total <= 0:
+                continue
+            packed = np.packbits(synth_bits("guard", total))
+            want_stego, _, _ = oc.embed_frames(frames, packed, total, delta, n)
+            for sc in (1, 3):
+                npx = nf * h * w * sc
+                buf = torch.full((guard + npx + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+                out = buf[guard:guard + npx].view((nf, h, w) if sc == 1 else (nf, h, w, 3))
+                res = svs_b200.embed_frames(_dev(frames), _dev(packed), total, delta, n, stego_channels=sc, out=out)
+                torch.cuda.synchronize()
+                assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + npx:] == 0xA5).all()), \
+                    "embed wrote outside the stego buffer %s n=%d sc=%d" % (shape, n, sc)
+                got = res.stego.cpu().numpy()
+                _assert_same_pixels(want_stego, got if sc == 1 else got[..., 0], "stego %s n=%d sc=%d" % (shape, n, sc))
+                if sc == 3:
+                    assert np.array_equal(got[..., 0], got[..., 1]) and np.array_equal(got[..., 0], got[..., 2])
+                pitch = svs_b200.bits_row_bytes(h, w, n)
+                bbuf = torch.full((guard + nf * pitch + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+                bout = bbuf[guard:guard + nf * pitch].view(nf, pitch)
+                ext = svs_b200.extract_frames(res.stego, delta, n, out=bout)
+                torch.cuda.synchronize()
+                assert bool((bbuf[:guard] == 0xA5).all()) and bool((bbuf[guard + nf * pitch:] == 0xA5).all()), \
+                    "extract wrote outside the bit rows %s n=%d" % (shape, n)
+                assert np.array_equal(oc.extract_frames(want_stego, delta, n), ext.cpu().numpy())
+
+
 def test_payload_bit_offset_and_tail_frames():
     frames = synth_frames("off", (6, 64, 96, 3))
     n, delta = 63, 20
