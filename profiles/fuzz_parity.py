@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time-bounded random parity run: the CUDA path against the plain-C oracle on random geometries,
-deltas, coefficient counts, payload lengths / bit offsets and frame contents.
+deltas, coefficient counts, payload lengths / bit offsets, frame contents, strided input views and both stego layouts.
 
 The -m gpu tests pin fixed cases (golden vectors, the delta x AC sweep, edge geometries); this
 script spends a fixed number of seconds on cases nobody wrote down, with the emphasis on what
@@ -89,14 +89,24 @@ def main():
         if a.dry:
             continue
         d_frames = torch.from_numpy(frames).to(dev)
+        if rng.random() < 0.3:                     # a strided view: rows and frames further apart than needed
+            wide = torch.zeros((f, h + 8, w + 16) + ((3,) if ch == 3 else ()), dtype=torch.uint8, device=dev)
+            view = wide[:, :h, 8:8 + w]
+            view.copy_(d_frames)
+            d_frames = view
         d_payload = torch.from_numpy(payload).to(dev)
-        res = svs_b200.embed_frames(d_frames, d_payload, total, delta, n, bit_offset=off, want_gray=True,
-                                    want_bits_embedded=True, want_sse=True)
-        got_bits = svs_b200.extract_frames(res.stego, delta, n)
+        sc = 3 if rng.random() < 0.3 else 1       # gray stego, or replicated to BGR as the FFV1 writer takes it
+        res = svs_b200.embed_frames(d_frames, d_payload, total, delta, n, bit_offset=off, stego_channels=sc,
+                                    want_gray=True, want_bits_embedded=True, want_sse=True)
+        got_bits = svs_b200.extract_frames(res.stego, delta, n)      # BGR stego: gray(g, g, g) = g
         torch.cuda.synchronize()
         nb = (cap + 7) // 8
+        got_stego = res.stego.cpu().numpy()
+        if sc == 3:
+            assert (got_stego[..., 0] == got_stego[..., 1]).all() and (got_stego[..., 0] == got_stego[..., 2]).all()
+            got_stego = got_stego[..., 0]
         diffs = {
-            "stego_px": int((res.stego.cpu().numpy() != want_stego).sum()),
+            "stego_px": int((got_stego != want_stego).sum()),
             "gray_px": int((res.gray.cpu().numpy() != want_gray).sum()),
             "bits_embedded": int((res.bits_embedded.cpu().numpy() != want_nbits).sum()),
             "sse": int((res.sse.cpu().numpy().astype(np.int64) != want_sse).sum()),

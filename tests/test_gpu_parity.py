@@ -350,7 +350,7 @@ def test_random_cases_against_oracle():
     """A few seconds of profiles/fuzz_parity.py: random geometries, deltas (integer, fractional, not
     float32), coefficient counts, payload ends / bit offsets and contents (saturated, flat, smooth,
     noise) - stego, gray, bits_embedded, SSE and extracted bits of every frame against the C oracle.
-    The committed 40 s run: profiles/r2_fuzz_parity.json (1,493 cases, 5,065 frames, 0 mismatches)."""
+    The committed runs: profiles/r2_fuzz_parity.json (2,686 cases, 9,066 frames, 0 mismatches)."""
     import importlib.util
     import os
     import sys
