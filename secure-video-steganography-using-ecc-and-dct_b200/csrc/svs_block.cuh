@@ -88,13 +88,7 @@ SVS_HD uint32_t magic_byte(uint32_t v, uint32_t magic_hi, int sel) { return hw::
 // weights are placed according to where the pixel's three bytes sit in the words (no shuffles).
 SVS_HD void bgr_row_sums(const uint32_t (&v)[6], uint32_t (&s)[8])
 {
-// SVS_BLK_PRMT1 (experiment, OFF): the rounding constant also carries 0x4B in the top byte and one
-// single-register PRMT makes the float (bgr_sum_to_float) - no magic-constant register, 35 MOVs
-// fewer per group.  MEASURED: slower (embed 1.613 vs 1.571 ms per 600 frames).
-#ifndef SVS_BLK_PRMT1
-#define SVS_BLK_PRMT1 0
-#endif
-    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u + (SVS_BLK_PRMT1 ? 0x4B000000u : 0u);
+    constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u, RND = 32768u;
 #pragma unroll
     for (int px = 0; px < 8; ++px) {
         const int byte0 = 3 * px, wi = byte0 >> 2, off = byte0 & 3;
@@ -104,10 +98,6 @@ SVS_HD void bgr_row_sums(const uint32_t (&v)[6], uint32_t (&s)[8])
         else               s[px] = hw::dp2a_lo((WR << 16) | WG, v[wi + 1], hw::dp2a_hi(WB << 16, v[wi], RND));
     }
 }
-
-// s = 0x4B | gray | 16 fraction bits  ->  bits of the float 2^23 + 256 * gray = [0x00, gray, 0x00, 0x4B]:
-// byte 3 as is, byte 2 to byte 1, and the two zero bytes as sign replication of byte 3 (0x4B < 0x80)
-SVS_HD uint32_t bgr_sum_to_float(uint32_t s) { return hw::prmt(s, s, 0x3B2Bu); }
 
 // 8 BGR pixels in six words -> their 8 gray bytes in two words
 SVS_HD void row_gray_words(const uint32_t* w, uint32_t& glo, uint32_t& ghi)
@@ -139,11 +129,7 @@ SVS_HD void row_to_pairs(const uint32_t* w, uint32_t magic_hi, P2* c, uint32_t& 
         bgr_row_sums(v, s);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-#if SVS_BLK_PRMT1
-            c[j] = hw::pku(bgr_sum_to_float(s[2 * j]), bgr_sum_to_float(s[2 * j + 1]));
-#else
             c[j] = hw::pku(hw::byte_perm(s[2 * j], magic_hi, 0x7524u), hw::byte_perm(s[2 * j + 1], magic_hi, 0x7524u));
-#endif
         if (WANT_GRAY) {
             glo = hw::byte_perm(hw::byte_perm(s[0], s[1], 0x0062u), hw::byte_perm(s[2], s[3], 0x0062u), 0x5410u);
             ghi = hw::byte_perm(hw::byte_perm(s[4], s[5], 0x0062u), hw::byte_perm(s[6], s[7], 0x0062u), 0x5410u);
@@ -184,15 +170,14 @@ SVS_HD void columns_fwd_pruned(const PackedOps& po, P2 (&c)[32])
 
 // rows 2i and 2i+1 of the column-pair layout (ra, rb: 4 pairs each) through scalar stage 1 ->
 // the eight stage-1 values of both rows, packed (lo = row 2i, hi = row 2i+1)
-// FAR: pair j of a row holds columns (j, j+4) instead of (2j, 2j+1) (see SVS_BLK_PAIRING)
-template <bool INVERSE, bool FAR = false>
+template <bool INVERSE>
 SVS_HD Stage1<P2> regroup_rows(const ScalarOps& so, const P2* ra, const P2* rb)
 {
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        hw::unpkf(ra[j], a[FAR ? j : 2 * j], a[FAR ? j + 4 : 2 * j + 1]);
-        hw::unpkf(rb[j], b[FAR ? j : 2 * j], b[FAR ? j + 4 : 2 * j + 1]);
+        hw::unpkf(ra[j], a[2 * j], a[2 * j + 1]);
+        hw::unpkf(rb[j], b[2 * j], b[2 * j + 1]);
     }
     const Stage1<float> ha = INVERSE ? svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7])
                                      : svs::dct8_fwd_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
@@ -209,27 +194,6 @@ SVS_HD void rows_fwd_pair(const PackedOps& po, const ScalarOps& so, const P2* c8
 {
     svs::dct8_fwd_tail(po, regroup_rows<false>(so, c8, c8 + 4), X);
 }
-// ... any two rows (4 column pairs each): X[v] = (coefficient (row a, v), coefficient (row b, v))
-SVS_HD void rows_fwd_two(const PackedOps& po, const ScalarOps& so, const P2* ra, const P2* rb, P2 (&X)[8])
-{
-    svs::dct8_fwd_tail(po, regroup_rows<false>(so, ra, rb), X);
-}
-
-// SVS_BLK_PAIRING = 1 (embed only): which rows / columns share a register pair is chosen so that
-// the SCALAR first stage of the two inverse passes never adds two registers of the same bank.
-// That stage combines inputs (1,7), (2,6), (3,5): with neighbours paired - (2i, 2i+1) - both sit in
-// the same half of their pairs, i.e. in registers of equal parity, and the add takes two
-// operand-delivery cycles instead of one (96 such adds per block).  With rows paired (i, i+4) for
-// the forward row pass / quantiser and columns paired (j, j+4) on the way out of the inverse
-// column pass, every one of them reads one even and one odd register.
-// MEASURED: slower (embed 1.544 vs 1.507 ms per 600 frames at 63 AC, 1.433 vs 1.370 at 10 AC) - two of
-// the three tie-prone coefficients move into the high halves and the register allocator needs more
-// moves; the bank conflicts it removes were not what limits the kernel.  OFF; both pairings are
-// compiled into the host tests (tests/test_block_host.py).
-#ifndef SVS_BLK_PAIRING
-#define SVS_BLK_PAIRING 0
-#endif
-constexpr bool kFarPairs = SVS_BLK_PAIRING != 0;
 
 // axis 0, inverse, columns 2j and 2j+1: reads the row-pair layout q, writes column pairs c[r*4+j]
 SVS_HD void columns_inv_pair(const PackedOps& po, const ScalarOps& so, const P2 (&q)[32], int j, P2 (&c)[32])
@@ -251,33 +215,10 @@ SVS_HD void columns_inv_pair(const PackedOps& po, const ScalarOps& so, const P2 
     for (int r = 0; r < 8; ++r) c[4 * r + j] = x[r];
 }
 
-// the same for the (i, i+4) row pairs / (j, j+4) column pairs of SVS_BLK_PAIRING: q[8i + col] =
-// (coefficient (i, col), coefficient (i+4, col)); transform j handles columns j and j+4 and writes
-// c[4r + j] = (x[r][j], x[r][j+4])
-SVS_HD void columns_inv_pair_far(const PackedOps& po, const ScalarOps& so, const P2 (&q)[32], int j, P2 (&c)[32])
-{
-    float a[8], b[8];                         // coefficient columns j and j+4, u = 0..7
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        hw::unpkf(q[8 * i + j], a[i], a[i + 4]);
-        hw::unpkf(q[8 * i + j + 4], b[i], b[i + 4]);
-    }
-    const Stage1<float> ha = svs::dct8_inv_head(so, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-    const Stage1<float> hb = svs::dct8_inv_head(so, b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    Stage1<P2> h;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) h.v[k] = hw::pk(ha.v[k], hb.v[k]);
-    P2 x[8];
-    svs::dct8_inv_tail(po, h, x);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) c[4 * r + j] = x[r];
-}
-
 // axis 1, inverse, rows 2i and 2i+1: out[col] = (pixel (2i, col), pixel (2i+1, col))
-template <bool FAR = false>
 SVS_HD void rows_inv_pair(const PackedOps& po, const ScalarOps& so, const P2* c8, P2 (&out)[8])
 {
-    svs::dct8_inv_tail(po, regroup_rows<true, FAR>(so, c8, c8 + 4), out);
+    svs::dct8_inv_tail(po, regroup_rows<true>(so, c8, c8 + 4), out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -373,11 +314,11 @@ SVS_RARE uint32_t fix_pair_extract(const P2* in, uint32_t rows, int i, int n, fl
 // 8u + v - 1 goes to coefficient (u, v): row-major flat index 1..n (config_and_setup.py:138-141).
 // p0/p1 are the window words pre-rotated so that bit idx sits `idx` places below position
 // erot: bringing it there is a rotate by the compile-time constant idx.
-template <bool NFULL, bool FAR>
+template <bool NFULL>
 SVS_HD void quant_embed_pair(int i, P2 (&X)[8], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t p0, uint32_t p1)
 {
-    // halves of pair v: coefficient rows (2i, 2i+1), or (i, i+4) with FAR
-    const int base = (FAR ? 8 : 16) * i - 1, hi_off = FAR ? 32 : 8;
+    // halves of pair v: coefficient rows 2i and 2i+1
+    const int base = 16 * i - 1, hi_off = 8;
     uint32_t worst = 0xffffffffu;
     P2 nx[8];
 #pragma unroll
@@ -478,13 +419,7 @@ SVS_HD void block_input(const uint32_t* rows, uint32_t magic_hi, P2 (&c)[32], ui
 
 // Forward 2-D transform of the block (column pairs c, destroyed) and embedding of its n payload
 // bits: q = the quantised coefficients as row pairs.  Every block coming here takes all n bits.
-// SVS_BLK_QPIPE (extract only, experiment, OFF): the axis-1 transform of row pair i+1 is issued before
-// row pair i is quantised, so that FP32 work and the quantiser's integer work sit in the same basic
-// block.  MEASURED: no gain (DESIGN.md / profiles/README.md).
-#ifndef SVS_BLK_QPIPE
-#define SVS_BLK_QPIPE 0
-#endif
-template <bool NFULL, bool FAR = kFarPairs>
+template <bool NFULL>
 SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, P2 (&q)[32])
 {
     const PackedOps po;
@@ -495,9 +430,8 @@ SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         P2 X[8];
-        if (FAR) rows_fwd_two(po, so, c + 4 * i, c + 4 * (i + 4), X);       // rows i and i+4
-        else rows_fwd_pair(po, so, c + 8 * i, X);                          // rows 2i and 2i+1
-        if (NFULL || (FAR ? 8 : 16) * i - 1 < n) quant_embed_pair<NFULL, FAR>(i, X, Q, n, w0, w1, p0, p1);
+        rows_fwd_pair(po, so, c + 8 * i, X);                               // rows 2i and 2i+1
+        if (NFULL || 16 * i - 1 < n) quant_embed_pair<NFULL>(i, X, Q, n, w0, w1, p0, p1);
 #pragma unroll
         for (int v = 0; v < 8; ++v) q[8 * i + v] = X[v];
     }
@@ -505,21 +439,17 @@ SVS_HD void block_forward_quant(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
 
 // Inverse 2-D transform of the row pairs q (destroyed) and conversion to bytes:
 // stego = 16 words, row r at [2r], [2r+1].
-template <bool FAR = kFarPairs>
 SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
 {
     const PackedOps po;
     const ScalarOps so;
     P2 c[32];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (FAR) columns_inv_pair_far(po, so, q, j, c);
-        else columns_inv_pair(po, so, q, j, c);
-    }
+    for (int j = 0; j < 4; ++j) columns_inv_pair(po, so, q, j, c);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         P2 o[8];
-        rows_inv_pair<FAR>(po, so, c + 8 * i, o);
+        rows_inv_pair(po, so, c + 8 * i, o);
         // clip then truncate (config_and_setup.py:171); low halves = row 2i, high halves = row 2i+1
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -529,21 +459,21 @@ SVS_HD void block_inverse(P2 (&q)[32], uint32_t* stego)
     }
 }
 
-template <bool NFULL, bool FAR = kFarPairs>
+template <bool NFULL>
 SVS_HD void block_embed_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t w0, uint32_t w1, uint32_t* stego)
 {
     P2 q[32];
-    block_forward_quant<NFULL, FAR>(c, Q, n, w0, w1, q);
-    block_inverse<FAR>(q, stego);
+    block_forward_quant<NFULL>(c, Q, n, w0, w1, q);
+    block_inverse(q, stego);
 }
 
-template <int CH, bool NFULL, bool WANT_GRAY, bool FAR = kFarPairs>
+template <int CH, bool NFULL, bool WANT_GRAY>
 SVS_HD void block_embed(const uint32_t* rows, uint32_t magic_hi, const QuantRegs& Q, int n, uint32_t w0, uint32_t w1,
                         uint32_t* stego, uint32_t* gray)
 {
     P2 c[32];
     block_input<CH, WANT_GRAY>(rows, magic_hi, c, gray);
-    block_embed_pairs<NFULL, FAR>(c, Q, n, w0, w1, stego);
+    block_embed_pairs<NFULL>(c, Q, n, w0, w1, stego);
 }
 
 // NP = number of coefficient row pairs that hold any of the n coefficients: ceil((n + 1) / 16).
@@ -558,17 +488,6 @@ SVS_HD void block_extract_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
     else columns_fwd_pruned<NP>(po, c);
     hi = 0;
     lo = 0;
-#if SVS_BLK_QPIPE
-    P2 X[2][8];
-    rows_fwd_pair(po, so, c, X[0]);
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        if (i + 1 < NP) rows_fwd_pair(po, so, c + 8 * (i + 1), X[(i + 1) & 1]);
-        const uint32_t rows2 = quant_extract_pair(i, X[i & 1], Q, n);
-        place_row(2 * i, rows2 & 0xffu, hi, lo);
-        place_row(2 * i + 1, rows2 >> 16, hi, lo);
-    }
-#else
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         P2 X[8];
@@ -577,7 +496,6 @@ SVS_HD void block_extract_pairs(P2 (&c)[32], const QuantRegs& Q, int n, uint32_t
         place_row(2 * i, rows2 & 0xffu, hi, lo);
         place_row(2 * i + 1, rows2 >> 16, hi, lo);
     }
-#endif
     // bits n.. of the string are not part of the stream (config_and_setup.py:138-140)
     if (n < 32) { hi &= ~(0xffffffffu >> n); lo = 0; }
     else if (n < 64) lo &= n == 32 ? 0u : ~(0xffffffffu >> (n - 32));
@@ -605,29 +523,22 @@ SVS_HD void block_extract(const uint32_t* rows, uint32_t magic_hi, const QuantRe
 #ifndef SVS_BLK_MIN_CTAS
 #define SVS_BLK_MIN_CTAS 1
 #endif
-// How the rows of a group reach the registers:
-//   0  LDG at the top of the group (the warp waits for HBM once per group);
-//   1  the same, plus prefetch.global.L2 of the NEXT group's rows;
-//   2  the next group's rows are requested as soon as the current ones have been converted to
-//      floats, with cp.async into a thread-private shared-memory slot (BGR input: 48 words,
-//      gray input: 16): they arrive while the current group is being transformed (default).
-#ifndef SVS_BLK_STAGE
-#define SVS_BLK_STAGE 2
-#endif
 constexpr int kBlkThreads = SVS_BLK_THREADS;
 constexpr int kBlkMinCtas = SVS_BLK_MIN_CTAS;
 constexpr int kBlkWarps = kBlkThreads / 32;
-constexpr int kBlkStage = SVS_BLK_STAGE;
 constexpr int kMaxPeers = 15;
 
-// Mode 2 stages through shared memory in every instantiation: a load in flight INTO REGISTERS
-// across the quantiser would make its rare out-of-line repair call wait for HBM (the callee
-// saves the registers the load is going to write) - measured: 8 % of the warp time.
+// How the rows of a group reach the registers: the NEXT group's rows are requested as soon as the
+// current ones have been converted to floats, with cp.async into a thread-private shared-memory
+// slot (BGR input: 48 words, gray input: 16); they arrive while the current group is being
+// transformed.  (Measured against LDG at the top of the group, with and without
+// prefetch.global.L2 of the next group: profiles/README.md.)  Every instantiation stages through
+// shared memory: a load in flight INTO REGISTERS across the quantiser would make its rare
+// out-of-line repair call wait for HBM (the callee saves the registers the load is going to
+// write) - measured: 8 % of the warp time.
+// Dynamic shared memory of a kernel instantiation: the cp.async slots, 8 bytes x rows x words x threads.
 template <int CH, bool EMBED>
-__host__ __device__ constexpr bool blk_uses_smem() { return kBlkStage == 2; }
-// dynamic shared memory of a kernel instantiation: the cp.async slots, 8 bytes x rows x words x threads
-template <int CH, bool EMBED>
-__host__ __device__ constexpr int blk_smem_bytes() { return blk_uses_smem<CH, EMBED>() ? 8 * (CH == 3 ? 3 : 1) * 8 * kBlkThreads : 0; }
+__host__ __device__ constexpr int blk_smem_bytes() { return 8 * (CH == 3 ? 3 : 1) * 8 * kBlkThreads; }
 // SIDE embed kernels park the block's 16 gray words in shared memory between the input stage and
 // the epilogue (16 registers the transforms need): word k of thread t at (k * kBlkThreads + t) * 4
 template <int CH, bool SIDE>
@@ -639,7 +550,7 @@ __host__ __device__ constexpr int blk_embed_smem_bytes() { return blk_smem_bytes
 struct BlkGeom {
     const uint8_t* frames;
     long long frame_stride, row_stride;
-    uint32_t frame_stride32, row_stride32;        // the same, when SVS_BLK_ADDR32 (the launcher checks that they fit)
+    uint32_t frame_stride32, row_stride32;        // the same as 32-bit values (the launcher checks that they fit)
     int bw, bpf, n;
     int gpf;                                      // groups per frame = ceil(bpf / 32)
     long long total_groups;                       // n_frames * gpf, < 2^31
@@ -693,12 +604,10 @@ __device__ __forceinline__ Where locate(const BlkGeom& G, long long g, int lane)
     return w;
 }
 
-// SVS_BLK_ADDR32: a frame spans less than 4 GB, so the offset of a block inside its frame and the
-// offsets of its 8 rows are 32-bit values (the row offsets r * stride are warp-uniform and loop-
-// invariant: uniform registers) - one 64-bit add per row instead of two, no 64-bit multiplies.
-#ifndef SVS_BLK_ADDR32
-#define SVS_BLK_ADDR32 1
-#endif
+// 32-bit addressing inside a frame: a frame spans less than 4 GB (svs_b200.cu: blk_addressable), so
+// the offset of a block inside its frame and the offsets of its 8 rows are 32-bit values (the row
+// offsets r * stride are warp-uniform and loop-invariant: uniform registers) - one 64-bit add per
+// row instead of two, no 64-bit multiplies.
 template <typename T>
 __device__ __forceinline__ T* frame_ptr(T* base, int f, uint32_t frame_stride, uint32_t in_frame)
 {
@@ -707,51 +616,12 @@ __device__ __forceinline__ T* frame_ptr(T* base, int f, uint32_t frame_stride, u
 template <int CH>
 __device__ __forceinline__ const uint8_t* block_src(const BlkGeom& G, const Where& w)
 {
-#if SVS_BLK_ADDR32
     return frame_ptr(G.frames, w.f, G.frame_stride32, (uint32_t)(w.by * 8) * G.row_stride32 + (uint32_t)(w.bx * (8 * CH)));
-#else
-    return G.frames + w.f * G.frame_stride + (long long)(w.by * 8) * G.row_stride + w.bx * (8 * CH);
-#endif
 }
 template <typename T>
-__device__ __forceinline__ T* row_ptr(T* p, int r, long long stride, uint32_t stride32)
+__device__ __forceinline__ T* row_ptr(T* p, int r, uint32_t stride32)
 {
-#if SVS_BLK_ADDR32
-    (void)stride;
     return p + (uint32_t)r * stride32;
-#else
-    (void)stride32;
-    return p + r * stride;
-#endif
-}
-
-template <int CH>
-__device__ __forceinline__ void load_rows(const BlkGeom& G, const Where& w, uint32_t* rows)
-{
-    constexpr int P = CH == 3 ? 3 : 1;
-    const uint8_t* p = block_src<CH>(G, w);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int j = 0; j < P; ++j) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + j);
-            rows[(r * P + j) * 2] = v.x;
-            rows[(r * P + j) * 2 + 1] = v.y;
-        }
-        p += G.row_stride;
-    }
-}
-
-// every 32-byte sector of the warp's 8 row spans holds the first byte of some lane's part
-template <int CH>
-__device__ __forceinline__ void prefetch_rows_l2(const BlkGeom& G, const Where& w)
-{
-    const uint8_t* p = block_src<CH>(G, w);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        p += G.row_stride;
-    }
 }
 
 // cp.async staging: slot (r, j) of thread t is 8 bytes at ((r*P + j) * kBlkThreads + t) * 8 of the
@@ -782,13 +652,13 @@ __device__ __forceinline__ void stage_request(const BlkGeom& G, const Where& w, 
 {
     const uint8_t* p = block_src<CH>(G, w);
     stage_request_row<CH, 0>(slot0, p);
-    stage_request_row<CH, 1>(slot0, row_ptr(p, 1, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 2>(slot0, row_ptr(p, 2, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 3>(slot0, row_ptr(p, 3, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 4>(slot0, row_ptr(p, 4, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 5>(slot0, row_ptr(p, 5, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 6>(slot0, row_ptr(p, 6, G.row_stride, G.row_stride32));
-    stage_request_row<CH, 7>(slot0, row_ptr(p, 7, G.row_stride, G.row_stride32));
+    stage_request_row<CH, 1>(slot0, row_ptr(p, 1, G.row_stride32));
+    stage_request_row<CH, 2>(slot0, row_ptr(p, 2, G.row_stride32));
+    stage_request_row<CH, 3>(slot0, row_ptr(p, 3, G.row_stride32));
+    stage_request_row<CH, 4>(slot0, row_ptr(p, 4, G.row_stride32));
+    stage_request_row<CH, 5>(slot0, row_ptr(p, 5, G.row_stride32));
+    stage_request_row<CH, 6>(slot0, row_ptr(p, 6, G.row_stride32));
+    stage_request_row<CH, 7>(slot0, row_ptr(p, 7, G.row_stride32));
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 template <int CH, int K>
@@ -814,7 +684,6 @@ struct PayWords {
 __device__ __forceinline__ PayWords payload_request(const uint32_t* __restrict__ words, long long last_word, long long pos)
 {
     PayWords p;
-#if SVS_BLK_ADDR32
     // word indices fit 32 bits (launcher), and the first word of a block the payload fills exists
     const uint32_t wi = (uint32_t)((unsigned long long)pos >> 5), left = (uint32_t)last_word - wi;
     const uint32_t* q = words + wi;
@@ -822,13 +691,6 @@ __device__ __forceinline__ PayWords payload_request(const uint32_t* __restrict__
     p.a = __ldg(q);
     p.b = left >= 1u ? __ldg(q + 1) : 0u;
     p.c = left >= 2u ? __ldg(q + 2) : 0u;
-#else
-    const long long wi = pos >> 5;
-    p.s = (uint32_t)(pos & 31);
-    p.a = wi <= last_word ? __ldg(words + wi) : 0u;
-    p.b = wi + 1 <= last_word ? __ldg(words + wi + 1) : 0u;
-    p.c = wi + 2 <= last_word ? __ldg(words + wi + 2) : 0u;
-#endif
     return p;
 }
 __device__ __forceinline__ void payload_window(const PayWords& p, uint32_t& w0, uint32_t& w1)
@@ -857,28 +719,6 @@ __device__ __forceinline__ void store_row(uint8_t* dst, uint32_t lo4, uint32_t h
 
 extern __shared__ __align__(16) unsigned char blk_dyn_smem[];
 
-// Work distribution inside a CTA (SVS_BLK_TICKETS).  The groups are dealt to the CTAs in rounds of
-// kBlkWarps consecutive groups (round j -> CTA j % gridDim.x), so that all CTAs sweep the batch
-// together; the warps of a CTA draw TICKETS from a shared-memory counter: ticket t = group
-// t % kBlkWarps of the CTA's round t / kBlkWarps.  With warps in step this is the static strided
-// assignment, but warps that get ahead take more tickets instead of finishing early.
-#ifndef SVS_BLK_PIN_D2
-#define SVS_BLK_PIN_D2 1
-#endif
-#ifndef SVS_BLK_TICKETS
-#define SVS_BLK_TICKETS 0
-#endif
-__device__ __forceinline__ long long ticket_group(unsigned t)
-{
-    return ((long long)(t / kBlkWarps) * gridDim.x + blockIdx.x) * kBlkWarps + (t % kBlkWarps);
-}
-__device__ __forceinline__ unsigned draw_ticket(unsigned* counter, int lane)
-{
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(counter, 1u);
-    return __shfl_sync(0xffffffffu, t, 0);
-}
-
 // SIDE: also the gray reference (first return value of the reference function,
 // config_and_setup.py:111-114,172) and / or the per-frame sum of squared differences gray vs
 // stego (what cv2.PSNR needs, embed_process.py:204-206), from the bytes the thread already holds.
@@ -889,7 +729,6 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = NFULL ? 63 : G.n;
     QuantRegs Q = make_quant_regs(a.q, G.delta32);
-#if SVS_BLK_PIN_D2
     {   // FFMA2 takes one uniform-register operand: with k0 there, 2*delta has to sit in a register.
         // Left alone ptxas re-creates it (MOV R, UR) in front of every one of the 32 FFMA2 of the
         // quantiser; an opaque move makes it a value that can only be kept.
@@ -899,17 +738,11 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
                      : "=r"(d2) : "r"((uint32_t)__cvta_generic_to_shared(&pin)), "r"(hw::f2u(a.q.d2)) : "memory");
         Q.d2 = hw::pku(d2, d2);
     }
-#endif
     // Plain kernels: warp i takes groups i, i + #warps, ... (all warps sweep the batch together).
     // SIDE kernels: warp i takes the CONTIGUOUS range [i K, (i+1) K) so that consecutive groups of a
     // warp belong to the same frame and its squared-error sum stays in a register until the frame
     // changes - one atomic per warp and frame instead of one per group (1013 same-address atomics
     // per 1080p frame cost 25 % of the kernel).
-#if SVS_BLK_TICKETS
-    __shared__ unsigned tickets;
-    if (threadIdx.x == 0) tickets = kBlkWarps;     // tickets 0 .. kBlkWarps-1 are the warps' first groups
-    __syncthreads();
-#endif
     const long long n_warps = (long long)gridDim.x * kBlkWarps;
     const long long my_warp = (long long)blockIdx.x * kBlkWarps + warp;
     const long long chunk = (G.total_groups + n_warps - 1) / n_warps;
@@ -917,9 +750,7 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
     long long g = SIDE ? my_warp * chunk : my_warp;
     const long long g_end = SIDE ? min(G.total_groups, g + chunk) : G.total_groups;
     if (g >= g_end) return;
-    constexpr bool kStaged = kBlkStage == 2;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(blk_dyn_smem) + threadIdx.x * 8u;
-    (void)slot0;
     unsigned long long sse_acc = 0;                // this warp's sum for frame sse_frame (lane 0 holds the total)
     int sse_frame = -1;
     (void)sse_acc; (void)sse_frame;
@@ -930,17 +761,10 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
     auto payload_pos = [&](const Where& x) {
         return a.payload_bit_offset + x.f * a.cap + (long long)min(x.base + lane, G.bpf - 1) * n;
     };
-    if (kStaged) {
-        stage_request<CH>(G, w, slot0);
-        pw = payload_request(a.payload, a.payload_last_word, payload_pos(w));
-    }
+    stage_request<CH>(G, w, slot0);
+    pw = payload_request(a.payload, a.payload_last_word, payload_pos(w));
     for (;;) {
-        if (!kStaged) {
-            load_rows<CH>(G, w, rows);
-            pw = payload_request(a.payload, a.payload_last_word, payload_pos(w));
-        } else {
-            stage_fetch<CH>(slot0, rows);
-        }
+        stage_fetch<CH>(slot0, rows);
         if (w.base + lane == 0 && a.bits_embedded != nullptr) a.bits_embedded[w.f] = a.cap;
         P2 c[32];
         uint32_t stego[16];
@@ -950,13 +774,9 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
             block_input<CH, SIDE>(rows, G.magic_hi, c, gray);
             if (SIDE) {
                 if (a.gray != nullptr && w.ok) {
-#if SVS_BLK_ADDR32
                     uint8_t* gd = frame_ptr(a.gray, w.f, (uint32_t)a.gray_frame_stride, (uint32_t)(w.by * 8) * (uint32_t)a.W + (uint32_t)(w.bx * 8));
-#else
-                    uint8_t* gd = a.gray + w.f * a.gray_frame_stride + (long long)(w.by * 8) * a.W + w.bx * 8;
-#endif
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) stg64(row_ptr(gd, r, a.W, (uint32_t)a.W), gray[2 * r], gray[2 * r + 1]);
+                    for (int r = 0; r < 8; ++r) stg64(row_ptr(gd, r, (uint32_t)a.W), gray[2 * r], gray[2 * r + 1]);
                 }
                 if (a.sse != nullptr) {
 #pragma unroll
@@ -968,35 +788,26 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) embed_blk_kernel(con
         payload_window(pw, w0, w1);
 
         // the next group of this warp: its rows (and payload words) are requested now
-#if SVS_BLK_TICKETS
-        const long long gn = SIDE ? g + 1 : ticket_group(draw_ticket(&tickets, lane));
-#else
         const long long gn = g + gstep;
-#endif
         const bool more = gn < g_end;
         Where wn = w;
         if (more) {
             wn = locate(G, gn, lane);
-            if (kStaged) stage_request<CH>(G, wn, slot0);
-            else if (kBlkStage == 1) prefetch_rows_l2<CH>(G, wn);
+            stage_request<CH>(G, wn, slot0);
         }
 
         P2 q[32];
         block_forward_quant<NFULL>(c, Q, n, w0, w1, q);
         // (only now: a load in flight across the quantiser would make its rare out-of-line repair
         // call wait for HBM - the callee saves the registers the load is going to write)
-        if (more && kStaged) pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
+        if (more) pw = payload_request(a.payload, a.payload_last_word, payload_pos(wn));
         block_inverse(q, stego);
         if (w.ok) {
-#if SVS_BLK_ADDR32
             uint8_t* dst = frame_ptr(a.stego, w.f, a.stego_frame_stride32,
                                      (uint32_t)(w.by * 8) * a.stego_row_stride32 + (uint32_t)(w.bx * (8 * OUT_CH)));
-#else
-            uint8_t* dst = a.stego + w.f * a.stego_frame_stride + (long long)(w.by * 8) * a.stego_row_stride + w.bx * (8 * OUT_CH);
-#endif
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-                store_row<OUT_CH>(row_ptr(dst, r, a.stego_row_stride, a.stego_row_stride32), stego[2 * r], stego[2 * r + 1]);
+                store_row<OUT_CH>(row_ptr(dst, r, a.stego_row_stride32), stego[2 * r], stego[2 * r + 1]);
         }
         if (SIDE) {
             if (a.sse != nullptr) {
@@ -1058,41 +869,27 @@ __global__ void __launch_bounds__(kBlkThreads, kBlkMinCtas) extract_blk_kernel(c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = NP == 4 ? (G.n >= 63 ? 63 : G.n) : G.n;
     const QuantRegs Q = make_quant_regs(a.q, G.delta32);
-#if SVS_BLK_TICKETS
-    __shared__ unsigned tickets;
-    if (threadIdx.x == 0) tickets = kBlkWarps;
-    __syncthreads();
-#endif
     const long long gstep = (long long)gridDim.x * kBlkWarps;
     long long g = (long long)blockIdx.x * kBlkWarps + warp;
     if (g >= G.total_groups) return;
-    constexpr bool kStaged = kBlkStage == 2;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(blk_dyn_smem) + threadIdx.x * 8u;
-    (void)slot0;
-    (void)gstep;
 
     Where w = locate(G, g, lane);
     uint32_t rows[CH == 3 ? 48 : 16];
-    if (kStaged) stage_request<CH>(G, w, slot0);
+    stage_request<CH>(G, w, slot0);
     for (;;) {
-        if (!kStaged) load_rows<CH>(G, w, rows);
-        else stage_fetch<CH>(slot0, rows);
+        stage_fetch<CH>(slot0, rows);
         pack[warp][lane] = 0;
         pack[warp][lane + 32] = 0;
         P2 c[32];
         block_input<CH, false>(rows, G.magic_hi, c, nullptr);
 
-#if SVS_BLK_TICKETS
-        const long long gn = ticket_group(draw_ticket(&tickets, lane));
-#else
         const long long gn = g + gstep;
-#endif
         const bool more = gn < G.total_groups;
         Where wn = w;
         if (more) {
             wn = locate(G, gn, lane);
-            if (kStaged) stage_request<CH>(G, wn, slot0);
-            else if (kBlkStage == 1) prefetch_rows_l2<CH>(G, wn);
+            stage_request<CH>(G, wn, slot0);
         }
 
         uint32_t hi, lo;

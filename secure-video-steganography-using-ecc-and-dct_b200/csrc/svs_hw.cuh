@@ -38,14 +38,6 @@ SVS_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 SVS_HD uint32_t f2u(float f) { return __float_as_uint(f); }
 SVS_HD float u2f(uint32_t u) { return __uint_as_float(u); }
 SVS_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
-// prmt.b32, default mode, all four selector bits: nibble & 7 picks a byte of (b:a), nibble & 8
-// replaces it by 8 copies of its sign bit (0x00 for a byte below 0x80: a free zero byte)
-SVS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
 SVS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 SVS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 SVS_HD uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { return __dp2a_lo(a, b, c); }
@@ -99,18 +91,6 @@ SVS_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel)
     const u64 src = (u64)a | ((u64)b << 32);
     uint32_t r = 0;
     for (int k = 0; k < 4; ++k) r |= (uint32_t)((src >> (8 * ((sel >> (4 * k)) & 7u))) & 0xffu) << (8 * k);
-    return r;
-}
-SVS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    const u64 src = (u64)a | ((u64)b << 32);
-    uint32_t r = 0;
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t nib = (sel >> (4 * k)) & 15u;
-        uint32_t byte = (uint32_t)((src >> (8 * (nib & 7u))) & 0xffu);
-        if (nib & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;
-        r |= byte << (8 * k);
-    }
     return r;
 }
 SVS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s)

@@ -34,7 +34,7 @@ def load():
     L.hm_quant_check.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
     u8p, c = ctypes.c_void_p, ctypes
     L.hm_blk_embed.restype = c.c_int
-    L.hm_blk_embed.argtypes = [c.c_int, u8p, c.c_long, c.c_double, c.c_int, u8p, u8p, u8p, c.c_int]
+    L.hm_blk_embed.argtypes = [c.c_int, u8p, c.c_long, c.c_double, c.c_int, u8p, u8p, u8p]
     L.hm_blk_extract.restype = c.c_int
     L.hm_blk_extract.argtypes = [c.c_int, u8p, c.c_long, c.c_double, c.c_int, u8p]
     return L

@@ -66,8 +66,7 @@ void bytes_of(const uint32_t* w16, uint8_t* out)
 
 extern "C" {
 // returns 0, or -1 when the packed quantiser does not cover this delta (the kernels then use the scalar path)
-// far != 0: the (i, i+4) row / (j, j+4) column pairing of SVS_BLK_PAIRING (same results by construction)
-int hm_blk_embed(int ch, const uint8_t* px, long nblocks, double delta, int n, const uint8_t* bits, uint8_t* stego, uint8_t* gray, int far)
+int hm_blk_embed(int ch, const uint8_t* px, long nblocks, double delta, int n, const uint8_t* bits, uint8_t* stego, uint8_t* gray)
 {
     const svs::FastQuant fq = svs::make_fast_quant(delta);
     if (!fq.embed_ok || (double)(float)delta != delta) return -1;
@@ -79,14 +78,9 @@ int hm_blk_embed(int ch, const uint8_t* px, long nblocks, double delta, int n, c
             if (i < 32) w0 |= (uint32_t)(bits[b * n + i] & 1) << (31 - i);
             else w1 |= (uint32_t)(bits[b * n + i] & 1) << (63 - i);
         }
-#define HM_E(CH, NF, FAR) blk::block_embed<CH, NF, true, FAR>(rows, 0x4B000000u, Q, n, w0, w1, s, g)
-        if (far) {
-            if (ch == 3) { if (n == 63) HM_E(3, true, true); else HM_E(3, false, true); }
-            else         { if (n == 63) HM_E(1, true, true); else HM_E(1, false, true); }
-        } else {
-            if (ch == 3) { if (n == 63) HM_E(3, true, false); else HM_E(3, false, false); }
-            else         { if (n == 63) HM_E(1, true, false); else HM_E(1, false, false); }
-        }
+#define HM_E(CH, NF) blk::block_embed<CH, NF, true>(rows, 0x4B000000u, Q, n, w0, w1, s, g)
+        if (ch == 3) { if (n == 63) HM_E(3, true); else HM_E(3, false); }
+        else         { if (n == 63) HM_E(1, true); else HM_E(1, false); }
 #undef HM_E
         bytes_of(s, stego + b * 64);
         bytes_of(g, gray + b * 64);
