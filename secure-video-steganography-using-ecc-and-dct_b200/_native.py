@@ -14,10 +14,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libsvs_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "svs_b200.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "svs_math.cuh"), os.path.join(_PKG, "csrc", "svs_quant.h"), os.path.join(_PKG, "csrc", "svs_fast.cuh"),
-           os.path.join(_PKG, "csrc", "svs_tile.cuh"), os.path.join(_PKG, "csrc", "svs_row.cuh"),
-           os.path.join(_PKG, "csrc", "svs_hw.cuh"), os.path.join(_PKG, "csrc", "svs_block.cuh"),
-           os.path.join(_ROOT, "include", "svs_b200.h")]
+HEADERS = [os.path.join(_PKG, "csrc", n) for n in ("svs_math.cuh", "svs_quant.h", "svs_hw.cuh", "svs_block.cuh")] + \
+          [os.path.join(_ROOT, "include", "svs_b200.h")]
+# the round-1 kernel organisations, only compiled into -DSVS_WITH_VARIANTS measurement builds
+VARIANT_HEADERS = [os.path.join(_PKG, "csrc", "variants", n) for n in ("svs_fast.cuh", "svs_tile.cuh", "svs_row.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

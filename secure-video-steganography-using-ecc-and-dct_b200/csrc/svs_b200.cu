@@ -25,9 +25,9 @@
 #include "svs_math.cuh"
 #include "svs_quant.h"
 #if defined(SVS_WITH_VARIANTS)
-#include "svs_fast.cuh"      // round-1 lockstep kernels (two blocks per thread)
-#include "svs_tile.cuh"      // measured dead ends, kept for the A/B script (profiles/build_variant.sh)
-#include "svs_row.cuh"
+#include "variants/svs_fast.cuh"      // round-1 lockstep kernels (two blocks per thread)
+#include "variants/svs_tile.cuh"      // measured dead ends, kept for the A/B script (profiles/build_variant.sh)
+#include "variants/svs_row.cuh"
 #endif
 #include "svs_block.cuh"
 

@@ -15,7 +15,7 @@
 //     FADD/FMUL (one lane per instruction, same pipe cycles per lane as the packed form), reads
 //     the halves where the previous pass left them and writes where the packed tail wants them;
 //   * a thread therefore owns 32 register pairs instead of 64: half the registers of the
-//     two-blocks-per-thread organisation of round 1 (svs_lockstep.cuh), twice the resident
+//     two-blocks-per-thread organisation of round 1 (variants/svs_fast.cuh), twice the resident
 //     warps, and a loop body of ~2 k instructions that fits the 32 KB instruction cache - the
 //     warps run free (no lockstep barrier) and their FP32-heavy transform phases overlap other
 //     warps' ALU-heavy quantiser / conversion phases.
